@@ -1,0 +1,196 @@
+"""CPU restatement of AcousticModel.inference.  Test infrastructure only.
+
+PARITY UNPINNED: jax / dm-haiku cannot be installed in this environment and the
+reference's tests (tests/test_nat_acoustic.py:9-18) hold no golden vectors, so
+this file restates the reference (file:line below, into /root/reference) using
+the published semantics of the dm-haiku modules it calls.  float64 mode is the
+arbiter for the float32 CUDA path.
+
+  TokenEncoder.__call__      vietTTS/nat/model.py:26-47
+  AcousticModel.prenet       vietTTS/nat/model.py:95-100
+  AcousticModel.upsample     vietTTS/nat/model.py:102-111
+  AcousticModel.postnet      vietTTS/nat/model.py:113-121
+  AcousticModel.inference    vietTTS/nat/model.py:123-144
+  predict_mel                vietTTS/nat/text2mel.py:61-82
+
+dm-haiku semantics used (not vendored in the reference, setup.py:6-19):
+  hk.LSTM            z=[x,h]W+b; i,g,f,o=split(z,4); c'=sigmoid(f+1)c+sigmoid(i)tanh(g); h'=sigmoid(o)tanh(c')
+  deep_rnn_with_skip_connections   layer1 input = concat(x, out0); output = concat(out0,out1)
+  hk.BatchNorm(eval) (x-mean_ema.average)*scale*rsqrt(var_ema.average+1e-5)+offset
+  hk.Conv1D          NWC, w[K,Cin,Cout], SAME zero padding
+  hk.dropout         keep*x/(1-rate); the keep mask is an explicit INPUT here
+                     (the reference draws it from the checkpoint's rng, model.py:97,99)
+  hk.ResetCore       state zeroed where reset is True, before the core runs
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+A = "acoustic_model/~/"
+T = A + "token_encoder/~/"
+
+
+def _t(a, dtype):
+    return torch.as_tensor(np.asarray(a)).to(dtype)
+
+
+def conv1d_same(x, w, b):
+    K = w.shape[0]
+    y = F.conv1d(x.transpose(1, 2), w.permute(2, 1, 0).contiguous(), b, padding=(K - 1) // 2)
+    return y.transpose(1, 2)
+
+
+def batchnorm_eval(x, P, S, name, dtype):
+    scale = _t(P[name]["scale"], dtype)
+    offset = _t(P[name]["offset"], dtype)
+    mean = _t(S[name + "/~/mean_ema"]["average"], dtype)
+    var = _t(S[name + "/~/var_ema"]["average"], dtype)
+    inv = scale * torch.rsqrt(var + 1e-5)
+    return (x - mean) * inv + offset
+
+
+def lstm_step(x, h, c, w, b):
+    """hk.LSTM.__call__"""
+    z = torch.cat([x, h], dim=-1) @ w + b
+    i, g, f, o = torch.chunk(z, 4, dim=-1)
+    f = torch.sigmoid(f + 1)
+    c = f * c + torch.sigmoid(i) * torch.tanh(g)
+    h = torch.sigmoid(o) * torch.tanh(c)
+    return h, c
+
+
+def token_encoder(P, S, tokens, lengths, dtype=torch.float32):
+    """model.py:26-47 with is_training=False.  tokens int [B,L]; lengths int [B].
+    Returns [B,L,2D]."""
+    tokens = torch.as_tensor(np.asarray(tokens)).long()
+    lengths = torch.as_tensor(np.asarray(lengths)).long()
+    x = _t(P[T + "embed"]["embeddings"], dtype)[tokens]
+    for i in range(3):
+        sfx = "" if i == 0 else f"_{i}"
+        cw = P[T + "conv1_d" + sfx]
+        x = conv1d_same(x, _t(cw["w"], dtype), _t(cw["b"], dtype))
+        x = torch.relu(batchnorm_eval(x, P, S, T + "batch_norm" + sfx, dtype))
+    B, L, D = x.shape
+    mask = torch.arange(L)[None, :] >= (lengths[:, None] - 1)  # model.py:37
+    wf, bf = _t(P[T + "lstm/linear"]["w"], dtype), _t(P[T + "lstm/linear"]["b"], dtype)
+    wb, bb = _t(P[T + "lstm_1/linear"]["w"], dtype), _t(P[T + "lstm_1/linear"]["b"], dtype)
+    h = x.new_zeros(B, D)
+    c = x.new_zeros(B, D)
+    fwd = []
+    for t in range(L):
+        h, c = lstm_step(x[:, t], h, c, wf, bf)
+        fwd.append(h)
+    h = x.new_zeros(B, D)
+    c = x.new_zeros(B, D)
+    bwd = [None] * L
+    for t in range(L - 1, -1, -1):  # flipped sequence, model.py:40-44
+        r = mask[:, t][:, None]
+        h = torch.where(r, torch.zeros_like(h), h)  # ResetCore
+        c = torch.where(r, torch.zeros_like(c), c)
+        h, c = lstm_step(x[:, t], h, c, wb, bb)
+        bwd[t] = h
+    return torch.cat([torch.stack(fwd, 1), torch.stack(bwd, 1)], dim=-1)
+
+
+def upsample(x, durations, n_frames: int):
+    """model.py:102-111.  x [B,L,D]; durations [B,L] in frames."""
+    ruler = torch.arange(0, n_frames, dtype=x.dtype)[None, :]
+    end_pos = torch.cumsum(durations, dim=1)
+    mid_pos = end_pos - durations / 2
+    d2 = torch.square(mid_pos[:, None, :] - ruler[:, :, None]) / 10.0
+    w = torch.softmax(-d2, dim=-1)
+    return torch.einsum("BLT,BTD->BLD", w, x), w
+
+
+def prenet(P, x, keep, dtype):
+    """model.py:95-100.  keep: None (dropout off, scale 1) or bool [B,2,256]."""
+    w1 = _t(P[A + "linear_1"]["w"], dtype)
+    w2 = _t(P[A + "linear_2"]["w"], dtype)
+    x = torch.relu(x @ w1)
+    if keep is not None:
+        x = keep[:, 0].to(dtype) * x / 0.5
+    x = torch.relu(x @ w2)
+    if keep is not None:
+        x = keep[:, 1].to(dtype) * x / 0.5
+    return x
+
+
+def decode(P, cond, masks=None, dtype=torch.float32):
+    """The hk.dynamic_unroll(loop_fn) of model.py:129-142.  cond [B,N,512];
+    masks uint8 [B,N,2,256] keep-masks or None.  Returns pre-postnet mel [B,N,80]."""
+    B, N, _ = cond.shape
+    w0, b0 = _t(P[A + "lstm/linear"]["w"], dtype), _t(P[A + "lstm/linear"]["b"], dtype)
+    w1, b1 = _t(P[A + "lstm_1/linear"]["w"], dtype), _t(P[A + "lstm_1/linear"]["b"], dtype)
+    wo, bo = _t(P[A + "linear"]["w"], dtype), _t(P[A + "linear"]["b"], dtype)
+    H = w0.shape[1] // 4
+    mel = cond.new_zeros(B, wo.shape[1])
+    h0 = cond.new_zeros(B, H)
+    c0 = cond.new_zeros(B, H)
+    h1 = cond.new_zeros(B, H)
+    c1 = cond.new_zeros(B, H)
+    if masks is not None:
+        masks = torch.as_tensor(np.asarray(masks)).bool()
+    out = []
+    for t in range(N):
+        p = prenet(P, mel, None if masks is None else masks[:, t], dtype)
+        x = torch.cat([cond[:, t], p], dim=-1)
+        h0, c0 = lstm_step(x, h0, c0, w0, b0)
+        h1, c1 = lstm_step(torch.cat([x, h0], dim=-1), h1, c1, w1, b1)
+        mel = torch.cat([h0, h1], dim=-1) @ wo + bo
+        out.append(mel)
+    return torch.stack(out, 1)
+
+
+def postnet(P, S, mel, dtype=torch.float32):
+    """model.py:113-121 with is_training=False."""
+    x = mel
+    for i in range(5):
+        sfx = "" if i == 0 else f"_{i}"
+        cw = P[A + "conv1_d" + sfx]
+        x = conv1d_same(x, _t(cw["w"], dtype), _t(cw["b"], dtype))
+        if i < 4:
+            x = torch.tanh(batchnorm_eval(x, P, S, A + "batch_norm" + sfx, dtype))
+    return x
+
+
+def inference(ckpt, tokens, durations_frames, n_frames: int, masks=None, dtype=torch.float32, taps=None):
+    """AcousticModel.inference (model.py:123-144).  tokens [B,L]; durations [B,L]
+    in frames; like the reference, `lengths=[L]` for every row."""
+    P, S = ckpt["params"], ckpt["aux"]
+    tokens = np.asarray(tokens)
+    B, L = tokens.shape
+    with torch.no_grad():
+        enc = token_encoder(P, S, tokens, np.full((B,), L), dtype)
+        cond, attn = upsample(enc, _t(durations_frames, dtype), n_frames)
+        x = decode(P, cond, masks, dtype)
+        res = postnet(P, S, x, dtype)
+        if taps is not None:
+            taps.update(enc=enc, cond=cond, attn=attn, pre=x, res=res)
+        return x + res
+
+
+def seconds_to_frames(durations_sec):
+    """text2mel.py:78-79: float32 `durations * 16000 / 256`, n_frames=int(sum)."""
+    d = (np.asarray(durations_sec, np.float32) * np.float32(16000)) / np.float32(256)
+    return d, int(np.sum(d, dtype=np.float32))
+
+
+def predict_mel(ckpt, tokens, durations_sec, masks=None, dtype=torch.float32):
+    """predict_mel (text2mel.py:61-82) minus the pickle load; returns np [N,80]."""
+    d, n = seconds_to_frames(durations_sec)
+    mel = inference(ckpt, np.asarray(tokens, np.int32)[None, :], d, n, masks, dtype)
+    return mel[0].numpy()
+
+
+def inference_ragged(ckpt, tokens_list, dur_frames_list, masks_list=None, dtype=torch.float32):
+    """Definition of batched semantics: row b of a batch equals
+    the reference run on row b alone, unpadded.  Returns list of np [N_b,80]."""
+    outs = []
+    for b, (tk, d) in enumerate(zip(tokens_list, dur_frames_list)):
+        d = np.asarray(d, np.float32)[None, :]
+        n = int(np.sum(d, dtype=np.float32))
+        m = None if masks_list is None else np.asarray(masks_list[b])[None, :n]
+        outs.append(inference(ckpt, np.asarray(tk, np.int32)[None, :], d, n, m, dtype)[0].numpy())
+    return outs
