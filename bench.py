@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the vietTTS hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): per GPU a batch of 32
+synthetic 100-phoneme / 5 s utterances (N = 312 mel frames, 79 872 samples each) goes through
+the NAT acoustic model (encoder, Gaussian upsampling, autoregressive decoder with prenet
+dropout, postnet) and the HiFiGAN generator.  One "step" = one such batch.  Weak scaling: every
+rank gets its own 32 utterances; the weights are broadcast once from rank 0 over NCCL.
+
+  value  : audio samples / s, whole job, inputs resident in HBM (device-pointer C ABI), CUDA events
+  e2e    : same metric through the host-buffer C ABI call (vtts_synthesize_host) with numpy inputs:
+           H2D of tokens/durations and D2H of the waveform inside the timed region
+  roofline: HiFiGAN generator (98 % of the FLOPs): algorithmic 614.1 MFLOP per mel frame / measured
+           stage time (CUDA events recorded around the stage inside the timed region)
+  cpu_baseline: the oracle port (torch CPU restatement of the reference) on the host cores,
+           bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+from viettts_b200 import config as C  # noqa: E402
+from viettts_b200 import synthetic  # noqa: E402
+
+METRIC = "audio_samples_per_sec"
+UNIT = "samples/s"
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_tflops=d.get("bf16_tflops", 1590.0),
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_batch(batch: int, phonemes: int, seconds: float, seed0: int):
+    toks, durs, nfs = [], [], []
+    for b in range(batch):
+        tk, d = synthetic.utterance(seed0 + b, phonemes, seconds)
+        d = (np.asarray(d, np.float32) * np.float32(C.SAMPLE_RATE)) / np.float32(C.HOP)
+        toks.append(np.asarray(tk, np.int32))
+        durs.append(d[0])
+        nfs.append(int(np.sum(d, dtype=np.float32)))
+    return np.stack(toks), np.stack(durs).astype(np.float32), np.asarray(nfs, np.int32)
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running beside the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle port) -- the only place bench.py executes oracle/
+# ---------------------------------------------------------------------------------------------
+def cpu_port_step(hp, ck, tokens, durs, nfs, masks):
+    """One pass of the reference algorithm (torch CPU restatement) over the given utterances."""
+    import torch
+    from oracle import hifigan_oracle, nat_oracle
+    n = int(nfs[0])
+    with torch.no_grad():
+        mel = nat_oracle.inference(ck, tokens, durs, n, masks)
+        wav = hifigan_oracle.generator_forward(hp, mel.numpy())
+    return int(wav.numel())
+
+
+def cpu_baseline(hp, ck, phonemes, seconds, budget_s=12.0, rows=2):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tokens, durs, nfs = make_batch(rows, phonemes, seconds, 9000)
+    masks = synthetic.dropout_masks(3, rows, int(nfs[0]))
+    cpu_port_step(hp, ck, tokens[:1], durs[:1], nfs[:1], masks[:1])  # warm-up
+    t0 = time.perf_counter()
+    samples, it = 0, 0
+    while True:
+        samples += cpu_port_step(hp, ck, tokens, durs, nfs, masks)
+        it += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=samples / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{it} passes of {rows} utterances ({phonemes} phonemes, {int(nfs[0])} frames) through oracle/ (torch CPU, {cores} threads), {dt:.1f} s")
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the
+    reference's JAX/Haiku path cannot be installed offline), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = synthetic.hifigan_params(1234)
+    ck = synthetic.acoustic_ckpt(1234)
+    rows = args.ref_rows
+    tokens, durs, nfs = make_batch(rows, args.phonemes, args.seconds, 0)
+    masks = synthetic.dropout_masks(3, rows, int(nfs[0]))
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_port_step(hp, ck, tokens, durs, nfs, masks)
+    t0 = time.perf_counter()
+    samples = 0
+    for _ in range(args.steps):
+        samples += cpu_port_step(hp, ck, tokens, durs, nfs, masks)
+    dt = time.perf_counter() - t0
+    val = samples / dt
+    out = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+               rtf=(dt / (samples / C.SAMPLE_RATE)),
+               config=dict(workload=f"NAT acoustic + HiFiGAN, {args.phonemes}-phoneme / {args.seconds:g} s utterances, batch {args.batch} per GPU",
+                           sample=f"{rows} utterances per step (bounded sample of the batch-{args.batch} workload)"),
+               cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
+                                 sample=f"{args.steps} steps x {rows} utterances through oracle/ (torch CPU restatement), {cores} threads"),
+               e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from viettts_b200 import parallel
+    from viettts_b200.engine import Engine
+
+    eng = Engine(local)
+    hp = synthetic.hifigan_params(1234) if rank == 0 else None
+    ck = synthetic.acoustic_ckpt(1234) if rank == 0 else None
+    t_w = time.perf_counter()
+    wbytes = parallel.load_weights_distributed(eng, hp, ck, dev)
+    t_w = time.perf_counter() - t_w
+
+    B = args.batch
+    tokens, durs, nfs = make_batch(B, args.phonemes, args.seconds, 1000 * rank)
+    N = int(nfs.max())
+    L = tokens.shape[1]
+    seed = 0xC0FFEE + rank
+    tok_t = torch.from_numpy(tokens).to(dev)
+    dur_t = torch.from_numpy(durs).to(dev)
+    nf_t = torch.from_numpy(nfs).to(dev)
+    mel_t = torch.empty((B, N, C.MEL_DIM), dtype=torch.float32, device=dev)
+    wav_t = torch.empty((B, N * C.HOP), dtype=torch.float32, device=dev)
+    samples_step = int(nfs.sum()) * C.HOP
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(marks=None):
+        if marks is not None:
+            marks[0].record()
+        eng.acoustic_forward(tok_t, dur_t, N, n_frames_t=nf_t, seed=seed, out=mel_t)
+        if marks is not None:
+            marks[1].record()
+        eng.hifigan_forward(mel_t, nf_t, out=wav_t)
+        if marks is not None:
+            marks[2].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    marks = [[ev(), ev(), ev()] for _ in range(args.steps)]
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(args.steps):
+        step(marks[k])
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    ac_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
+    hg_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * samples_step / (ms_step / 1e3)
+
+    # ---- e2e through the host-buffer C ABI ----
+    for _ in range(2):
+        eng.synthesize(tokens, durs, n_frames=nfs, seed=seed)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wav_h = eng.synthesize(tokens, durs, n_frames=nfs, seed=seed)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_val = world * samples_step * args.steps / dt
+    h2d = tokens.nbytes + durs.nbytes + nfs.nbytes
+    d2h = wav_h.nbytes
+
+    if rank == 0:
+        pk = peaks()
+        frames = int(nfs.sum())
+        flops = frames * C.HIFIGAN_FLOP_PER_FRAME
+        ach = flops / (hg_ms / 1e3) / 1e12
+        out = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            rtf=(ms_step / 1e3) / (world * samples_step / C.SAMPLE_RATE),
+            config=dict(workload=f"NAT acoustic + HiFiGAN, {args.phonemes}-phoneme / {args.seconds:g} s utterances, batch {B} per GPU (BASELINE configs[2])",
+                        batch_per_gpu=B, phonemes=L, mel_frames=N, samples_per_utterance=N * C.HOP, parallelism=f"utterance-sharded x{world}",
+                        l2="activations per step (>4 GB) exceed the 126 MB L2; no flush needed", dropout="on-device threefry keep-masks"),
+            stages_ms=dict(acoustic=ac_ms, hifigan=hg_ms),
+            e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt / args.steps,
+                     api="vtts_synthesize_host via viettts_b200.Engine.synthesize (numpy in, numpy out)"),
+            gpu_launches=int(launches),
+            roofline=dict(bound="tensor", kernel="HiFiGAN generator stage (conv1d_nwc_kernel launches + conv_post)", achieved=ach,
+                          peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_tflops_sustained"], traffic=None,
+                          peak_source=pk["source"] + ", sustained bf16 dense",
+                          note="strict-fp32 path runs on the FP32 FMA pipe (nominal 74 TFLOP/s); fraction is quoted against the tensor peak"),
+            clocks=clocks, weights=dict(bytes=wbytes, broadcast_s=t_w),
+        )
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(synthetic.hifigan_params(1234), synthetic.acoustic_ckpt(1234), args.phonemes, args.seconds)
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--phonemes", type=int, default=100)
+    ap.add_argument("--seconds", type=float, default=5.0)
+    ap.add_argument("--ref-rows", type=int, default=2, help="utterances per step of the CPU reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+/*
+ * viettts_b200.h -- C ABI of the B200-native vietTTS hot path (libviettts_b200.so).
+ *
+ * The reference (NTT123/vietTTS) has no FFI: its seams for this path are three
+ * Python callables.  Each entry point below names the reference interface it
+ * replaces (file:line into the reference tree):
+ *
+ *   vietTTS/hifigan/mel2wave.py:20-41     mel2wave(mel)            -> vtts_mel2wave_host / vtts_hifigan_forward
+ *   vietTTS/nat/text2mel.py:61-82         predict_mel(tok, dur)    -> vtts_predict_mel_host / vtts_acoustic_forward
+ *   vietTTS/nat/dsp.py:104-128            MelFilter(...)(y)        -> vtts_melspec_host / vtts_melspec
+ *   vietTTS/hifigan/mel2wave.py:35-36     pickle.load(hk_hifi)     -> vtts_load_hifigan
+ *   vietTTS/nat/text2mel.py:62-71         pickle.load(acoustic)    -> vtts_load_acoustic
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (`stream` is a
+ *     cudaStream_t passed as void*, NULL = default stream).
+ *   - every call returns 0 on success or a negative vtts_status; the message is
+ *     available from vtts_last_error().  Nothing throws across the ABI.  There is
+ *     NO CPU fallback: without a usable sm_100 device vtts_create fails.
+ *   - one context per GPU; a context is not thread-safe; `*_forward` calls are
+ *     stream-ordered and asynchronous, `*_host` calls copy H2D/D2H through pinned
+ *     staging owned by the context and return after the result is in host memory.
+ *   - "dev" pointers are device memory owned by the caller (e.g. torch tensors'
+ *     data_ptr()), float32 unless stated, dense row-major in the documented shape.
+ *   - tensors are NWC ([batch, time, channels]) exactly like the Haiku models.
+ */
+#ifndef VIETTTS_B200_H
+#define VIETTTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vtts_ctx vtts_ctx;
+
+typedef enum vtts_status {
+  VTTS_OK = 0,
+  VTTS_ERR_BAD_ARG = -1,
+  VTTS_ERR_CUDA = -2,
+  VTTS_ERR_NOT_LOADED = -3,   /* weights for this stage were not loaded */
+  VTTS_ERR_NO_DEVICE = -4,    /* no CUDA device / not an sm_100 part */
+  VTTS_ERR_OOM = -5
+} vtts_status;
+
+/* dropout handling for the prenet (vietTTS/nat/model.py:95-100: dropout is live at inference) */
+typedef enum vtts_dropout_mode {
+  VTTS_DROPOUT_OFF = 0,     /* deterministic parity mode: no mask, scale 1 */
+  VTTS_DROPOUT_MASK = 1,    /* caller supplies uint8 keep-mask [B,N,2,256]; kept values are scaled by 2 */
+  VTTS_DROPOUT_SEED = 2     /* keep bits drawn on device from threefry2x32(seed; b,t,layer,unit) */
+} vtts_dropout_mode;
+
+/* ---- library / context ------------------------------------------------------------ */
+int vtts_version(void);                                  /* ABI version, currently 1 */
+int vtts_create(int device, vtts_ctx** out);
+int vtts_destroy(vtts_ctx* ctx);
+const char* vtts_last_error(vtts_ctx* ctx);              /* ctx may be NULL: last error of failed create */
+int vtts_device_info(vtts_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+
+/* ---- weights --------------------------------------------------------------------------
+ * A "blob" is the float32 concatenation of the Haiku-layout tensors in the canonical order
+ * listed in INTEGRATION.md (viettts_b200/weights.py builds it from the unchanged pickles).
+ * `blob` may be a host or a device pointer (detected); device blobs let rank != 0 load
+ * weights received by an NCCL broadcast without a host round trip. */
+int64_t vtts_hifigan_blob_floats(void);                  /* 13 926 017 */
+int64_t vtts_acoustic_blob_floats(void);                 /* params + BatchNorm eval statistics */
+int vtts_load_hifigan(vtts_ctx* ctx, const float* blob, int64_t n_floats);
+int vtts_load_acoustic(vtts_ctx* ctx, const float* blob, int64_t n_floats);
+/* librosa-style filterbank [80][513] (MelFilter.__init__, dsp.py:107-113) */
+int vtts_load_mel_filterbank(vtts_ctx* ctx, const float* fb, int n_mels, int n_bins);
+
+/* ---- device-pointer, stream-ordered entry points ---------------------------------------- */
+
+/* Generator.__call__ (vietTTS/hifigan/model.py:109-125).
+ * mel_dev [B,T,80]; n_frames_dev int32 [B] or NULL (= T for every row; rows are zero-padded
+ * at their true end); wav_dev [B,256*T] (samples past 256*n_frames[b] are 0). */
+int vtts_hifigan_forward(vtts_ctx* ctx, const float* mel_dev, const int32_t* n_frames_dev,
+                         int B, int T, float* wav_dev, void* stream);
+
+/* AcousticModel.inference (vietTTS/nat/model.py:123-144).
+ * tokens_dev int32 [B,L]; lengths_dev int32 [B] or NULL (= L); dur_frames_dev [B,L] durations in
+ * FRAMES (seconds*62.5); n_frames_dev int32 [B] or NULL (= N); keep_mask_dev uint8 [B,N,2,256]
+ * (mode MASK) or NULL; mel_dev [B,N,80] (rows past n_frames[b] are 0).
+ * Row b equals the reference run on row b alone (batch semantics the reference lacks). */
+int vtts_acoustic_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev,
+                          const float* dur_frames_dev, const int32_t* n_frames_dev,
+                          const uint8_t* keep_mask_dev, int dropout_mode, uint64_t seed,
+                          int B, int L, int N, float* mel_dev, void* stream);
+
+/* MelFilter.__call__ (vietTTS/nat/dsp.py:115-128). wav_dev [B,S], S % 256 == 0, S >= 512;
+ * mel_dev [B,S/256,80]. */
+int vtts_melspec(vtts_ctx* ctx, const float* wav_dev, int B, int S, float* mel_dev, void* stream);
+
+/* optional taps for tests: copy an internal activation of the LAST forward call to host.
+ * name: "enc" [B,L,512], "cond" [B,N,512], "mel_pre" [B,N,80] (before the postnet). */
+int vtts_debug_read(vtts_ctx* ctx, const char* name, float* host_out, int64_t n_floats);
+
+/* ---- host-buffer entry points (what a ctypes / cgo / JNI binding calls) ------------------ */
+int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav);
+int vtts_predict_mel_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths,
+                          const float* dur_frames, const int32_t* n_frames,
+                          const uint8_t* keep_mask, int dropout_mode, uint64_t seed,
+                          int B, int L, int N, float* mel);
+/* predict_mel -> mel2wave without leaving the device: tokens/durations in, waveform out */
+int vtts_synthesize_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths,
+                         const float* dur_frames, const int32_t* n_frames,
+                         const uint8_t* keep_mask, int dropout_mode, uint64_t seed,
+                         int B, int L, int N, float* mel_out_or_null, float* wav);
+int vtts_melspec_host(vtts_ctx* ctx, const float* wav, int B, int S, float* mel);
+
+/* ---- introspection for bench / tests ------------------------------------------------------ */
+/* number of kernel launches issued by this context since creation (our kernels only) */
+int64_t vtts_launch_count(vtts_ctx* ctx);
+/* elapsed ms of the last forward call of the given stage, measured with CUDA events on the
+ * stream the kernels were launched on: stage 0 = hifigan, 1 = acoustic, 2 = melspec.
+ * Synchronises the stream. */
+int vtts_last_stage_ms(vtts_ctx* ctx, int stage, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIETTTS_B200_H */

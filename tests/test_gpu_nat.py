@@ -1,0 +1,151 @@
+"""GPU parity: NAT acoustic model (CUDA, through the C ABI) vs the CPU restatement.
+
+The oracle for this stage is UNPINNED (no jax/haiku here; see oracle/__init__.py).
+Tolerance (fp32, shared dropout masks): mel L-inf <= 1e-3 (log-mel units) after the
+full autoregressive scan; encoder/upsample taps <= 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nat_oracle as no
+from viettts_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+MEL_LINF = 1e-3
+
+
+@pytest.fixture(scope="module")
+def eng(acoustic_ckpt):
+    from viettts_b200.engine import Engine
+    e = Engine(0)
+    e.load_acoustic(acoustic_ckpt)
+    yield e
+    e.close()
+
+
+def _utt(seed, L, seconds):
+    tokens, dur = synthetic.utterance(seed, L, seconds)
+    d, n = no.seconds_to_frames(dur)
+    return np.asarray(tokens, np.int32), d[0], n
+
+
+def test_small_utterance_all_taps(eng, acoustic_ckpt):
+    tk, d, n = _utt(0, 20, 0.5)
+    masks = synthetic.dropout_masks(42, 1, n)
+    mel = eng.predict_mel(tk[None], d[None], n_frames=[n], masks=masks)
+    taps = {}
+    ref = no.inference(acoustic_ckpt, tk[None], d[None], n, masks, taps=taps).numpy()
+    enc = eng.debug_read("enc", (1, 20, 512))
+    cond = eng.debug_read("cond", (1, n, 512))
+    pre = eng.debug_read("mel_pre", (1, n, 80))
+    e_enc = np.abs(enc - taps["enc"].numpy()).max()
+    e_cond = np.abs(cond - taps["cond"].numpy()).max()
+    e_pre = np.abs(pre - taps["pre"].numpy()).max()
+    e_mel = np.abs(mel - ref).max()
+    print(f"enc {e_enc:.3e} cond {e_cond:.3e} pre {e_pre:.3e} mel {e_mel:.3e}")
+    assert e_enc < 1e-4 and e_cond < 1e-4
+    assert e_pre < MEL_LINF and e_mel < MEL_LINF
+
+
+def test_c1_100_phonemes_5s(eng, acoustic_ckpt):
+    """BASELINE config 1 shape: 100 phonemes, 312 frames, shared masks."""
+    tk, d, n = _utt(0, 100, 5.0)
+    assert n == 312
+    masks = synthetic.dropout_masks(42, 1, n)
+    mel = eng.predict_mel(tk[None], d[None], n_frames=[n], masks=masks)
+    ref = no.inference(acoustic_ckpt, tk[None], d[None], n, masks).numpy()
+    ref64 = no.inference(acoustic_ckpt, tk[None], d[None], n, masks, dtype=torch.float64).numpy()
+    print(f"C1: gpu-vs-f32 {np.abs(mel-ref).max():.3e}  gpu-vs-f64 {np.abs(mel-ref64).max():.3e}  f32-vs-f64 {np.abs(ref-ref64).max():.3e}")
+    assert np.abs(mel - ref64).max() < MEL_LINF
+
+
+def test_dropout_off_mode(eng, acoustic_ckpt):
+    tk, d, n = _utt(3, 30, 1.0)
+    mel = eng.predict_mel(tk[None], d[None], n_frames=[n])
+    ref = no.inference(acoustic_ckpt, tk[None], d[None], n, None).numpy()
+    assert np.abs(mel - ref).max() < MEL_LINF
+
+
+def _threefry2x32(k0, k1, c0, c1):
+    """numpy restatement of the device generator (csrc/nat.cu) for the SEED mode check."""
+    M = np.uint32
+    k0, k1, c0, c1 = (np.asarray(v, dtype=np.uint32) for v in (k0, k1, c0, c1))
+    ks = [k0, k1, M(0x1BD11BDA) ^ k0 ^ k1]
+    x0, x1 = c0 + k0, c1 + k1
+    R = [[13, 15, 26, 6], [17, 29, 16, 24]]
+    with np.errstate(over="ignore"):
+        for blk in range(5):
+            for r in R[blk & 1]:
+                x0 = x0 + x1
+                x1 = (x1 << M(r)) | (x1 >> M(32 - r))
+                x1 = x1 ^ x0
+            x0 = x0 + ks[(blk + 1) % 3]
+            x1 = x1 + ks[(blk + 2) % 3] + M(blk + 1)
+    return x0, x1
+
+
+def test_seed_mode_matches_documented_stream(eng, acoustic_ckpt):
+    tk, d, n = _utt(4, 25, 0.8)
+    seed = (7 << 32) | 12345
+    mel = eng.predict_mel(tk[None], d[None], n_frames=[n], seed=seed)
+    t = np.arange(n, dtype=np.uint32)[:, None, None]
+    lu = (np.arange(2, dtype=np.uint32)[None, :, None] * 256 + np.arange(256, dtype=np.uint32)[None, None, :])
+    o0, _ = _threefry2x32(np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32), t + 0 * lu, lu + 0 * t)
+    masks = (o0 < np.uint32(0x80000000)).astype(np.uint8)[None]
+    assert 0.4 < masks.mean() < 0.6
+    ref = no.inference(acoustic_ckpt, tk[None], d[None], n, masks).numpy()
+    assert np.abs(mel - ref).max() < MEL_LINF
+    again = eng.predict_mel(tk[None], d[None], n_frames=[n], seed=seed)
+    assert np.array_equal(mel, again)
+
+
+def test_ragged_batch_equals_single_rows(eng, acoustic_ckpt):
+    """Batched semantics: row b == reference run on row b alone."""
+    utts = [_utt(10, 12, 0.3), _utt(11, 31, 1.1), _utt(12, 20, 0.7), _utt(13, 5, 0.2)]
+    B = len(utts)
+    Lmax = max(len(u[0]) for u in utts)
+    tokens = np.zeros((B, Lmax), np.int32)
+    dur = np.zeros((B, Lmax), np.float32)
+    lens = np.array([len(u[0]) for u in utts], np.int32)
+    nfs = np.array([u[2] for u in utts], np.int32)
+    for b, (tk, d, n) in enumerate(utts):
+        tokens[b, : len(tk)] = tk
+        dur[b, : len(tk)] = d
+    N = int(nfs.max())
+    masks = synthetic.dropout_masks(5, B, N)
+    mel = eng.predict_mel(tokens, dur, lengths=lens, n_frames=nfs, masks=masks)
+    refs = no.inference_ragged(acoustic_ckpt, [u[0] for u in utts], [u[1] for u in utts], [masks[b] for b in range(B)])
+    for b in range(B):
+        e = np.abs(mel[b, : nfs[b]] - refs[b]).max()
+        print(f"row {b}: L={lens[b]} N={nfs[b]} err {e:.3e}")
+        assert e < MEL_LINF
+        assert np.all(mel[b, nfs[b] :] == 0.0)
+
+
+def test_batch32_rows_independent(eng, acoustic_ckpt):
+    """Config-3 size (B=32, L=100, N=312): every row must equal that row run alone (bit exact:
+    same kernels, same reduction order), and one row is checked against the oracle."""
+    B = 32
+    utts = [_utt(100 + b, 100, 5.0) for b in range(B)]
+    tokens = np.stack([u[0] for u in utts])
+    dur = np.stack([u[1] for u in utts])
+    nfs = np.array([u[2] for u in utts], np.int32)
+    assert (nfs == 312).all()
+    masks = synthetic.dropout_masks(9, B, 312)
+    mel = eng.predict_mel(tokens, dur, n_frames=nfs, masks=masks)
+    assert np.isfinite(mel).all()
+    for b in (0, 13, 31):
+        alone = eng.predict_mel(tokens[b : b + 1], dur[b : b + 1], n_frames=nfs[b : b + 1], masks=masks[b : b + 1])
+        assert np.abs(alone[0] - mel[b]).max() < 1e-5
+    ref = no.inference(acoustic_ckpt, tokens[7:8], dur[7:8], 312, masks[7:8]).numpy()
+    assert np.abs(mel[7] - ref[0]).max() < MEL_LINF
+
+
+def test_synthesize_equals_two_stage(eng, acoustic_ckpt, hifigan_params):
+    eng.load_hifigan(hifigan_params)
+    tk, d, n = _utt(0, 16, 0.4)
+    masks = synthetic.dropout_masks(1, 1, n)
+    wav, mel = eng.synthesize(tk[None], d[None], n_frames=[n], masks=masks, return_mel=True)
+    mel2 = eng.predict_mel(tk[None], d[None], n_frames=[n], masks=masks)
+    assert np.array_equal(mel, mel2)
+    assert np.array_equal(wav, eng.mel2wave(mel2))

@@ -1,0 +1,489 @@
+// C ABI of libviettts_b200.so (see include/viettts_b200.h for the contract and the reference
+// interfaces each entry point replaces).
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "vtts_internal.cuh"
+
+std::string g_vtts_create_error;
+
+int vtts_ctx::fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  err = buf;
+  return code;
+}
+
+int vtts_ctx::ensure_ws(size_t bytes) {
+  vtts_ctx* ctx = this;
+  if (bytes <= ws_bytes) return VTTS_OK;
+  if (ws) {
+    VTTS_CUDA(cudaDeviceSynchronize());
+    cudaFree(ws);
+    ws = nullptr;
+    ws_bytes = 0;
+  }
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&ws, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&ws, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ws = nullptr;
+    return fail(VTTS_ERR_OOM, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+  }
+  ws_bytes = want;
+  return VTTS_OK;
+}
+
+int vtts_ctx::ensure_staging(size_t host_bytes, size_t dev_bytes) {
+  vtts_ctx* ctx = this;
+  if (host_bytes > hpin_bytes) {
+    if (hpin) cudaFreeHost(hpin);
+    hpin = nullptr;
+    hpin_bytes = 0;
+    VTTS_CUDA(cudaMallocHost(&hpin, host_bytes));
+    hpin_bytes = host_bytes;
+  }
+  if (dev_bytes > dstage_bytes) {
+    if (dstage) {
+      VTTS_CUDA(cudaDeviceSynchronize());
+      cudaFree(dstage);
+    }
+    dstage = nullptr;
+    dstage_bytes = 0;
+    cudaError_t e = cudaMalloc(&dstage, dev_bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(VTTS_ERR_OOM, "device staging of %zu bytes: %s", dev_bytes, cudaGetErrorString(e));
+    }
+    dstage_bytes = dev_bytes;
+  }
+  return VTTS_OK;
+}
+
+// ---- canonical blob layouts ------------------------------------------------------------------------
+const std::vector<TensorSpec>& vtts_hifigan_specs() {
+  static std::vector<TensorSpec> s;
+  if (!s.empty()) return s;
+  s.push_back({"conv_pre.w[7,80,512]", 7 * 80 * 512});
+  s.push_back({"conv_pre.b", 512});
+  int C = 512;
+  for (int i = 0; i < 4; ++i) {
+    s.push_back({"ups.w[K,C/2,C]", (int64_t)vc::hg_upk(i) * (C / 2) * C});
+    s.push_back({"ups.b", C / 2});
+    C /= 2;
+  }
+  C = 256;
+  for (int n = 0; n < 12; ++n) {
+    const int k = vc::hg_rbk(n % 3);
+    const int ch = 256 >> (n / 3);
+    for (int which = 0; which < 2; ++which)
+      for (int m = 0; m < 3; ++m) {
+        s.push_back({"resblock.conv.w[k,C,C]", (int64_t)k * ch * ch});
+        s.push_back({"resblock.conv.b", ch});
+      }
+  }
+  s.push_back({"conv_post.w[7,32,1]", 7 * 32});
+  s.push_back({"conv_post.b", 1});
+  return s;
+}
+
+const std::vector<TensorSpec>& vtts_acoustic_specs() {
+  static std::vector<TensorSpec> s;
+  if (!s.empty()) return s;
+  s.push_back({"embed[256,256]", 256 * 256});
+  for (int i = 0; i < 3; ++i) {
+    s.push_back({"enc.conv.w[3,256,256]", 3 * 256 * 256});
+    s.push_back({"enc.conv.b", 256});
+    s.push_back({"enc.bn.scale", 256});
+    s.push_back({"enc.bn.offset", 256});
+    s.push_back({"enc.bn.mean", 256});
+    s.push_back({"enc.bn.var", 256});
+  }
+  for (int d = 0; d < 2; ++d) {
+    s.push_back({"enc.lstm.w[512,1024]", 512 * 1024});
+    s.push_back({"enc.lstm.b", 1024});
+  }
+  s.push_back({"dec.lstm0.w[1280,2048]", 1280 * 2048});
+  s.push_back({"dec.lstm0.b", 2048});
+  s.push_back({"dec.lstm1.w[1792,2048]", 1792 * 2048});
+  s.push_back({"dec.lstm1.b", 2048});
+  s.push_back({"proj.w[1024,80]", 1024 * 80});
+  s.push_back({"proj.b", 80});
+  s.push_back({"prenet.fc1.w[80,256]", 80 * 256});
+  s.push_back({"prenet.fc2.w[256,256]", 256 * 256});
+  const int dims[6] = {80, 512, 512, 512, 512, 80};
+  for (int i = 0; i < 5; ++i) {
+    s.push_back({"postnet.conv.w[5,cin,cout]", (int64_t)5 * dims[i] * dims[i + 1]});
+    s.push_back({"postnet.conv.b", dims[i + 1]});
+    if (i < 4) {
+      s.push_back({"postnet.bn.scale", 512});
+      s.push_back({"postnet.bn.offset", 512});
+      s.push_back({"postnet.bn.mean", 512});
+      s.push_back({"postnet.bn.var", 512});
+    }
+  }
+  return s;
+}
+
+static int64_t total_floats(const std::vector<TensorSpec>& s) {
+  int64_t t = 0;
+  for (auto& e : s) t += e.n;
+  return t;
+}
+
+// copy a contiguous blob (host or device) into per-tensor 256B-aligned device slots
+static int load_blob(vtts_ctx* ctx, const std::vector<TensorSpec>& specs, const float* blob, int64_t n_floats, float** store,
+                     std::vector<float*>& ptrs) {
+  if (!blob) return ctx->fail(VTTS_ERR_BAD_ARG, "load: null blob");
+  if (n_floats != total_floats(specs))
+    return ctx->fail(VTTS_ERR_BAD_ARG, "load: blob has %lld floats, expected %lld", (long long)n_floats, (long long)total_floats(specs));
+  size_t total = 0;
+  std::vector<size_t> offs(specs.size());
+  for (size_t i = 0; i < specs.size(); ++i) {
+    offs[i] = total;
+    total += ((size_t)specs[i].n + 63) & ~size_t(63);
+  }
+  if (*store) {
+    VTTS_CUDA(cudaDeviceSynchronize());
+    cudaFree(*store);
+    *store = nullptr;
+  }
+  VTTS_CUDA(cudaMalloc(store, total * sizeof(float)));
+  VTTS_CUDA(cudaMemset(*store, 0, total * sizeof(float)));
+  ptrs.resize(specs.size());
+  int64_t src = 0;
+  for (size_t i = 0; i < specs.size(); ++i) {
+    ptrs[i] = *store + offs[i];
+    VTTS_CUDA(cudaMemcpy(ptrs[i], blob + src, (size_t)specs[i].n * sizeof(float), cudaMemcpyDefault));
+    src += specs[i].n;
+  }
+  return VTTS_OK;
+}
+
+extern "C" {
+
+int vtts_version(void) { return 1; }
+
+int vtts_create(int device, vtts_ctx** out) {
+  if (!out) {
+    g_vtts_create_error = "vtts_create: out is NULL";
+    return VTTS_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_vtts_create_error = std::string("vtts_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    cudaGetLastError();
+    return VTTS_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    g_vtts_create_error = "vtts_create: device index out of range";
+    return VTTS_ERR_BAD_ARG;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_vtts_create_error = std::string("vtts_create: ") + cudaGetErrorString(e);
+    return VTTS_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "vtts_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    g_vtts_create_error = buf;
+    return VTTS_ERR_NO_DEVICE;
+  }
+  vtts_ctx* ctx = new vtts_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->hbm_bytes = prop.totalGlobalMem;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_vtts_create_error = std::string("vtts_create: ") + cudaGetErrorString(e);
+    delete ctx;
+    return VTTS_ERR_CUDA;
+  }
+  for (int i = 0; i < 3; ++i) {
+    cudaEventCreate(&ctx->ev0[i]);
+    cudaEventCreate(&ctx->ev1[i]);
+  }
+  *out = ctx;
+  return VTTS_OK;
+}
+
+int vtts_destroy(vtts_ctx* ctx) {
+  if (!ctx) return VTTS_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(ctx->hg_blob); cudaFree(ctx->hg_upsw); cudaFree(ctx->ac_blob); cudaFree(ctx->ac_derived);
+  cudaFree(ctx->mel_fb); cudaFree(ctx->mel_lo); cudaFree(ctx->mel_hi); cudaFree(ctx->fft_tw); cudaFree(ctx->hann);
+  cudaFree(ctx->ws); cudaFree(ctx->dstage);
+  if (ctx->hpin) cudaFreeHost(ctx->hpin);
+  for (int i = 0; i < 3; ++i) {
+    cudaEventDestroy(ctx->ev0[i]);
+    cudaEventDestroy(ctx->ev1[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return VTTS_OK;
+}
+
+const char* vtts_last_error(vtts_ctx* ctx) { return ctx ? ctx->err.c_str() : g_vtts_create_error.c_str(); }
+
+int vtts_device_info(vtts_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (hbm_bytes) *hbm_bytes = (int64_t)ctx->hbm_bytes;
+  return VTTS_OK;
+}
+
+int64_t vtts_hifigan_blob_floats(void) { return total_floats(vtts_hifigan_specs()); }
+int64_t vtts_acoustic_blob_floats(void) { return total_floats(vtts_acoustic_specs()); }
+
+int vtts_load_hifigan(vtts_ctx* ctx, const float* blob, int64_t n_floats) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  ctx->hg_loaded = false;
+  int rc = load_blob(ctx, vtts_hifigan_specs(), blob, n_floats, &ctx->hg_blob, ctx->hg_t);
+  if (rc) return rc;
+  rc = vtts_hifigan_prepare(ctx);
+  if (rc) return rc;
+  ctx->hg_loaded = true;
+  return VTTS_OK;
+}
+
+int vtts_load_acoustic(vtts_ctx* ctx, const float* blob, int64_t n_floats) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  ctx->ac_loaded = false;
+  int rc = load_blob(ctx, vtts_acoustic_specs(), blob, n_floats, &ctx->ac_blob, ctx->ac_t);
+  if (rc) return rc;
+  rc = vtts_acoustic_prepare(ctx);
+  if (rc) return rc;
+  ctx->ac_loaded = true;
+  return VTTS_OK;
+}
+
+int vtts_load_mel_filterbank(vtts_ctx* ctx, const float* fb, int n_mels, int n_bins) {
+  if (!ctx || !fb) return VTTS_ERR_BAD_ARG;
+  if (n_mels != vc::MEL || n_bins != vc::NBINS) return ctx->fail(VTTS_ERR_BAD_ARG, "mel filterbank must be [80][513], got [%d][%d]", n_mels, n_bins);
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  ctx->mel_loaded = false;
+  if (!ctx->mel_fb) VTTS_CUDA(cudaMalloc(&ctx->mel_fb, (size_t)vc::MEL * vc::NBINS * sizeof(float)));
+  VTTS_CUDA(cudaMemcpy(ctx->mel_fb, fb, (size_t)vc::MEL * vc::NBINS * sizeof(float), cudaMemcpyDefault));
+  int rc = vtts_melspec_prepare(ctx);
+  if (rc) return rc;
+  ctx->mel_loaded = true;
+  return VTTS_OK;
+}
+
+static void stage_begin(vtts_ctx* ctx, int stage, cudaStream_t st) {
+  cudaEventRecord(ctx->ev0[stage], st);
+  ctx->ev_stream[stage] = st;
+}
+static void stage_end(vtts_ctx* ctx, int stage, cudaStream_t st) {
+  cudaEventRecord(ctx->ev1[stage], st);
+  ctx->ev_valid[stage] = true;
+}
+
+int vtts_hifigan_forward(vtts_ctx* ctx, const float* mel_dev, const int32_t* n_frames_dev, int B, int T, float* wav_dev, void* stream) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!mel_dev || !wav_dev) return ctx->fail(VTTS_ERR_BAD_ARG, "hifigan_forward: null pointer");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  stage_begin(ctx, 0, st);
+  int rc = vtts_hifigan_run(ctx, mel_dev, n_frames_dev, B, T, wav_dev, st);
+  stage_end(ctx, 0, st);
+  return rc;
+}
+
+int vtts_acoustic_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev, const float* dur_frames_dev,
+                          const int32_t* n_frames_dev, const uint8_t* keep_mask_dev, int dropout_mode, uint64_t seed, int B, int L,
+                          int N, float* mel_dev, void* stream) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!tokens_dev || !dur_frames_dev || !mel_dev) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic_forward: null pointer");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need = 0;
+  int rc = vtts_acoustic_run(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, B, L, N, nullptr, st, nullptr, 0, &need);
+  if (rc) return rc;
+  // the acoustic workspace lives after the hifigan one is released: both share ctx->ws, so a
+  // synthesize call sizes it for the larger of the two (see vtts_synthesize_host)
+  rc = ctx->ensure_ws(need);
+  if (rc) return rc;
+  stage_begin(ctx, 1, st);
+  rc = vtts_acoustic_run(ctx, tokens_dev, lengths_dev, dur_frames_dev, n_frames_dev, keep_mask_dev, dropout_mode, seed, B, L, N,
+                         mel_dev, st, ctx->ws, ctx->ws_bytes, nullptr);
+  stage_end(ctx, 1, st);
+  return rc;
+}
+
+int vtts_melspec(vtts_ctx* ctx, const float* wav_dev, int B, int S, float* mel_dev, void* stream) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!wav_dev || !mel_dev) return ctx->fail(VTTS_ERR_BAD_ARG, "melspec: null pointer");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  stage_begin(ctx, 2, st);
+  int rc = vtts_melspec_run(ctx, wav_dev, B, S, mel_dev, st);
+  stage_end(ctx, 2, st);
+  return rc;
+}
+
+int vtts_debug_read(vtts_ctx* ctx, const char* name, float* host_out, int64_t n_floats) {
+  if (!ctx || !name || !host_out) return VTTS_ERR_BAD_ARG;
+  const float* src = nullptr;
+  int64_t n = 0;
+  if (!strcmp(name, "enc")) { src = ctx->tap_enc; n = ctx->tap_enc_n; }
+  else if (!strcmp(name, "cond")) { src = ctx->tap_cond; n = ctx->tap_cond_n; }
+  else if (!strcmp(name, "mel_pre")) { src = ctx->tap_melpre; n = ctx->tap_melpre_n; }
+  else return ctx->fail(VTTS_ERR_BAD_ARG, "debug_read: unknown tap %s", name);
+  if (!src || n_floats != n) return ctx->fail(VTTS_ERR_BAD_ARG, "debug_read: tap %s has %lld floats, asked %lld", name, (long long)n, (long long)n_floats);
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  VTTS_CUDA(cudaDeviceSynchronize());
+  VTTS_CUDA(cudaMemcpy(host_out, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return VTTS_OK;
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+// Layout of the staging areas: inputs first, outputs after, every block 256B aligned; the same
+// offsets are used in the pinned host buffer and in the device staging buffer.
+namespace {
+struct Stager {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    return o;
+  }
+};
+}  // namespace
+
+int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!mel || !wav || B < 1 || T < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "mel2wave_host: bad argument");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  Stager s;
+  const size_t mel_b = (size_t)B * T * vc::MEL * 4, nf_b = (size_t)B * 4, wav_b = (size_t)B * T * vc::HOP * 4;
+  const size_t o_mel = s.take(mel_b), o_nf = s.take(nf_b), o_wav = s.take(wav_b);
+  int rc = ctx->ensure_staging(s.off, s.off);
+  if (rc) return rc;
+  char* hp = (char*)ctx->hpin;
+  char* dp = (char*)ctx->dstage;
+  cudaStream_t st = ctx->own_stream;
+  memcpy(hp + o_mel, mel, mel_b);
+  if (n_frames) memcpy(hp + o_nf, n_frames, nf_b);
+  VTTS_CUDA(cudaMemcpyAsync(dp + o_mel, hp + o_mel, (n_frames ? o_nf + nf_b : mel_b) - o_mel, cudaMemcpyHostToDevice, st));
+  rc = vtts_hifigan_forward(ctx, (const float*)(dp + o_mel), n_frames ? (const int32_t*)(dp + o_nf) : nullptr, B, T, (float*)(dp + o_wav), st);
+  if (rc) return rc;
+  VTTS_CUDA(cudaMemcpyAsync(hp + o_wav, dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  memcpy(wav, hp + o_wav, wav_b);
+  return VTTS_OK;
+}
+
+static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur, const int32_t* n_frames,
+                        const uint8_t* keep, int mode, uint64_t seed, int B, int L, int N, float* mel_out, float* wav_out) {
+  if (!tokens || !dur || B < 1 || L < 1 || N < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "predict_mel/synthesize_host: bad argument");
+  if (mode == VTTS_DROPOUT_MASK && !keep) return ctx->fail(VTTS_ERR_BAD_ARG, "dropout_mode MASK needs keep_mask");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  Stager s;
+  const size_t tok_b = (size_t)B * L * 4, len_b = (size_t)B * 4, dur_b = (size_t)B * L * 4, nf_b = (size_t)B * 4;
+  const size_t keep_b = mode == VTTS_DROPOUT_MASK ? (size_t)B * N * 2 * vc::PRENET : 0;
+  const size_t mel_b = (size_t)B * N * vc::MEL * 4, wav_b = wav_out ? (size_t)B * N * vc::HOP * 4 : 0;
+  const size_t o_tok = s.take(tok_b), o_len = s.take(len_b), o_dur = s.take(dur_b), o_nf = s.take(nf_b), o_keep = s.take(keep_b);
+  const size_t in_end = s.off;
+  const size_t o_mel = s.take(mel_b), o_wav = s.take(wav_b);
+  int rc = ctx->ensure_staging(s.off, s.off);
+  if (rc) return rc;
+  char* hp = (char*)ctx->hpin;
+  char* dp = (char*)ctx->dstage;
+  cudaStream_t st = ctx->own_stream;
+  memcpy(hp + o_tok, tokens, tok_b);
+  if (lengths) memcpy(hp + o_len, lengths, len_b);
+  memcpy(hp + o_dur, dur, dur_b);
+  if (n_frames) memcpy(hp + o_nf, n_frames, nf_b);
+  if (keep_b) memcpy(hp + o_keep, keep, keep_b);
+  VTTS_CUDA(cudaMemcpyAsync(dp, hp, in_end, cudaMemcpyHostToDevice, st));
+  const int32_t* d_len = lengths ? (const int32_t*)(dp + o_len) : nullptr;
+  const int32_t* d_nf = n_frames ? (const int32_t*)(dp + o_nf) : nullptr;
+  rc = vtts_acoustic_forward(ctx, (const int32_t*)(dp + o_tok), d_len, (const float*)(dp + o_dur), d_nf,
+                             keep_b ? (const uint8_t*)(dp + o_keep) : nullptr, mode, seed, B, L, N, (float*)(dp + o_mel), st);
+  if (rc) return rc;
+  if (mel_out) VTTS_CUDA(cudaMemcpyAsync(hp + o_mel, dp + o_mel, mel_b, cudaMemcpyDeviceToHost, st));
+  if (wav_out) {
+    // the hifigan workspace replaces the acoustic one: its kernels are stream-ordered after the acoustic ones,
+    // but growing the workspace frees memory -> make sure `mel` (in dstage) is complete first
+    size_t need = vtts_hifigan_ws_bytes(B, N);
+    if (need > ctx->ws_bytes) VTTS_CUDA(cudaStreamSynchronize(st));
+    rc = vtts_hifigan_forward(ctx, (const float*)(dp + o_mel), d_nf, B, N, (float*)(dp + o_wav), st);
+    if (rc) return rc;
+    VTTS_CUDA(cudaMemcpyAsync(hp + o_wav, dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
+  }
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  if (mel_out) memcpy(mel_out, hp + o_mel, mel_b);
+  if (wav_out) memcpy(wav_out, hp + o_wav, wav_b);
+  return VTTS_OK;
+}
+
+int vtts_predict_mel_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur_frames,
+                          const int32_t* n_frames, const uint8_t* keep_mask, int dropout_mode, uint64_t seed, int B, int L, int N,
+                          float* mel) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!mel) return ctx->fail(VTTS_ERR_BAD_ARG, "predict_mel_host: null output");
+  return synth_common(ctx, tokens, lengths, dur_frames, n_frames, keep_mask, dropout_mode, seed, B, L, N, mel, nullptr);
+}
+
+int vtts_synthesize_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur_frames,
+                         const int32_t* n_frames, const uint8_t* keep_mask, int dropout_mode, uint64_t seed, int B, int L, int N,
+                         float* mel_out_or_null, float* wav) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!wav) return ctx->fail(VTTS_ERR_BAD_ARG, "synthesize_host: null output");
+  return synth_common(ctx, tokens, lengths, dur_frames, n_frames, keep_mask, dropout_mode, seed, B, L, N, mel_out_or_null, wav);
+}
+
+int vtts_melspec_host(vtts_ctx* ctx, const float* wav, int B, int S, float* mel) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!wav || !mel || B < 1 || S < 512 || S % vc::HOP) return ctx->fail(VTTS_ERR_BAD_ARG, "melspec_host: bad argument");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  Stager s;
+  const size_t wav_b = (size_t)B * S * 4, mel_b = (size_t)B * (S / vc::HOP) * vc::MEL * 4;
+  const size_t o_wav = s.take(wav_b), o_mel = s.take(mel_b);
+  int rc = ctx->ensure_staging(s.off, s.off);
+  if (rc) return rc;
+  char* hp = (char*)ctx->hpin;
+  char* dp = (char*)ctx->dstage;
+  cudaStream_t st = ctx->own_stream;
+  memcpy(hp + o_wav, wav, wav_b);
+  VTTS_CUDA(cudaMemcpyAsync(dp + o_wav, hp + o_wav, wav_b, cudaMemcpyHostToDevice, st));
+  rc = vtts_melspec(ctx, (const float*)(dp + o_wav), B, S, (float*)(dp + o_mel), st);
+  if (rc) return rc;
+  VTTS_CUDA(cudaMemcpyAsync(hp + o_mel, dp + o_mel, mel_b, cudaMemcpyDeviceToHost, st));
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  memcpy(mel, hp + o_mel, mel_b);
+  return VTTS_OK;
+}
+
+int64_t vtts_launch_count(vtts_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vtts_last_stage_ms(vtts_ctx* ctx, int stage, float* ms) {
+  if (!ctx || !ms || stage < 0 || stage > 2) return VTTS_ERR_BAD_ARG;
+  if (!ctx->ev_valid[stage]) return ctx->fail(VTTS_ERR_BAD_ARG, "last_stage_ms: stage %d has not run", stage);
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  VTTS_CUDA(cudaEventSynchronize(ctx->ev1[stage]));
+  VTTS_CUDA(cudaEventElapsedTime(ms, ctx->ev0[stage], ctx->ev1[stage]));
+  return VTTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// Internal declarations shared by the translation units of libviettts_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/viettts_b200.h"
+
+// ---- model constants (vietTTS/nat/config.py:8-59, assets/hifigan/config.json:2-28) ----------
+namespace vc {
+constexpr int MEL = 80;
+constexpr int HOP = 256;
+constexpr int NFFT = 1024;
+constexpr int NBINS = 513;
+constexpr int ENC_D = 256;        // acoustic_encoder_dim
+constexpr int ENC_OUT = 512;      // BiLSTM concat
+constexpr int DEC_H = 512;        // acoustic_decoder_dim
+constexpr int PRENET = 256;
+constexpr int POSTNET = 512;
+constexpr int VOCAB = 256;
+constexpr int HG_C0 = 512;        // upsample_initial_channel
+constexpr int HG_NSTAGE = 4;
+__host__ __device__ constexpr int hg_rate(int i) { return i < 2 ? 8 : 2; }
+__host__ __device__ constexpr int hg_upk(int i) { return i < 2 ? 16 : 4; }
+__host__ __device__ constexpr int hg_rbk(int j) { return j == 0 ? 3 : (j == 1 ? 7 : 11); }
+__host__ __device__ constexpr int hg_dil(int m) { return m == 0 ? 1 : (m == 1 ? 3 : 5); }
+}  // namespace vc
+
+#define VTTS_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      return ctx->fail(VTTS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,               \
+                       cudaGetErrorString(_e));                                                  \
+    }                                                                                            \
+  } while (0)
+
+// ---- generic NWC conv problem description (conv1d.cu) ----------------------------------------
+struct ConvProb {
+  const float* x0;       // input  [B][rows_in][Cin]
+  const float* x1;       // extra inputs for pre_mode 2 (sum of three / 3), else null
+  const float* x2;
+  const float* w;        // [k][Cin][Cout]
+  const float* bias;     // [Cout]
+  const float* resid;    // [B][rows_out][Cout] or null, added after the activation
+  const float* bn_mean;  // eval BatchNorm (all four or none): y = (y-mean)*inv + off
+  const float* bn_inv;   //   inv = scale*rsqrt(var+1e-5) precomputed at load
+  const float* bn_off;
+  float* out;            // [B][rows_out][Cout]
+  int k, dil, in_off;    // input row of tap j for output index tau: tau + j*dil + in_off
+  int out_stride, out_off;  // output row = tau*out_stride + out_off (transposed-conv phases)
+};
+
+struct ConvLaunch {
+  ConvProb p[8];
+  int nprob;
+  int Cin, Cout;
+  int B;
+  int T_rows;         // tau range per batch row (== allocated input rows)
+  int rows_out;       // allocated output rows per batch row
+  const int* len;     // int32 [B] or null
+  int len_mul;        // valid tau < len[b]*len_mul (clamped to T_rows)
+  int pre_mode;       // 0 none, 1 leaky_relu(pre_slope), 2 (x0+x1+x2)/3 then leaky_relu(pre_slope)
+  float pre_slope;
+  int post_act;       // 0 none, 1 tanh, 2 relu
+};
+
+struct vtts_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t hbm_bytes = 0;
+  std::string err;
+  int64_t launches = 0;
+  cudaStream_t own_stream = nullptr;   // used by the *_host entry points
+
+  // ---- weights (device) ----
+  float* hg_blob = nullptr;     // haiku-layout tensors, each 256B aligned inside the arena
+  std::vector<float*> hg_t;     // tensor pointers in canonical order
+  float* hg_upsw = nullptr;     // transposed-conv weights repacked per output phase
+  bool hg_loaded = false;
+
+  float* ac_blob = nullptr;
+  std::vector<float*> ac_t;
+  float* ac_derived = nullptr;  // bn inv, repacked recurrent weights, ...
+  std::vector<float*> ac_d;
+  bool ac_loaded = false;
+
+  // mel filterbank + fft tables
+  float* mel_fb = nullptr;      // dense [80][513]
+  int* mel_lo = nullptr;        // [80] first non-zero bin
+  int* mel_hi = nullptr;        // [80] one past last non-zero bin
+  float* fft_tw = nullptr;      // [1024][2] cos/sin(-2 pi k/1024)
+  float* hann = nullptr;        // [1024]
+  bool mel_loaded = false;
+
+  // ---- workspace (device), grown on demand ----
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // pinned host staging + device staging for *_host calls
+  void* hpin = nullptr;
+  size_t hpin_bytes = 0;
+  void* dstage = nullptr;
+  size_t dstage_bytes = 0;
+
+  // taps of the last acoustic forward (point into ws)
+  float* tap_enc = nullptr; int64_t tap_enc_n = 0;
+  float* tap_cond = nullptr; int64_t tap_cond_n = 0;
+  float* tap_melpre = nullptr; int64_t tap_melpre_n = 0;
+
+  cudaEvent_t ev0[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev1[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t ev_stream[3] = {nullptr, nullptr, nullptr};
+  bool ev_valid[3] = {false, false, false};
+
+  int fail(int code, const char* fmt, ...);
+  int ensure_ws(size_t bytes);
+  int ensure_staging(size_t host_bytes, size_t dev_bytes);
+};
+
+extern std::string g_vtts_create_error;
+
+// bump allocator over the context workspace
+struct Arena {
+  char* base;
+  size_t off = 0;
+  size_t cap;
+  bool measure;  // if true only compute the size
+  Arena(void* b, size_t c, bool m) : base((char*)b), cap(c), measure(m) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = measure ? nullptr : (T*)(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// conv1d.cu
+int vtts_launch_conv(vtts_ctx* ctx, const ConvLaunch& L, cudaStream_t st);
+// hifigan.cu
+int vtts_hifigan_prepare(vtts_ctx* ctx);   // derived weights after load
+int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav, cudaStream_t st);
+size_t vtts_hifigan_ws_bytes(int B, int T);
+// nat.cu
+int vtts_acoustic_prepare(vtts_ctx* ctx);
+int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur,
+                      const int32_t* n_frames, const uint8_t* keep, int mode, uint64_t seed, int B, int L, int N,
+                      float* mel, cudaStream_t st, void* ws_base, size_t ws_cap, size_t* ws_need);
+// melspec.cu
+int vtts_melspec_prepare(vtts_ctx* ctx);
+int vtts_melspec_run(vtts_ctx* ctx, const float* wav, int B, int S, float* mel, cudaStream_t st);
+
+// canonical blob layouts (weights.cu)
+struct TensorSpec { const char* name; int64_t n; };
+const std::vector<TensorSpec>& vtts_hifigan_specs();
+const std::vector<TensorSpec>& vtts_acoustic_specs();
+
+// indices into ctx->hg_t  (canonical order: pre, ups 0..3, resblocks 0..11 x (c1_0,c1_1,c1_2,c2_0,c2_1,c2_2), post)
+namespace hgi {
+constexpr int PRE_W = 0, PRE_B = 1;
+__host__ __device__ constexpr int UPS_W(int i) { return 2 + 2 * i; }
+__host__ __device__ constexpr int UPS_B(int i) { return 3 + 2 * i; }
+// resblock n (0..11), which: 0 = convs1, 1 = convs2, m = 0..2
+__host__ __device__ constexpr int RB_W(int n, int which, int m) { return 10 + n * 12 + (which * 3 + m) * 2; }
+__host__ __device__ constexpr int RB_B(int n, int which, int m) { return RB_W(n, which, m) + 1; }
+constexpr int POST_W = 10 + 12 * 12, POST_B = POST_W + 1;
+constexpr int COUNT = POST_B + 1;
+}  // namespace hgi
+
+// indices into ctx->ac_t
+namespace aci {
+constexpr int EMBED = 0;
+// encoder conv i: w, b, bn_scale, bn_offset, bn_mean, bn_var
+__host__ __device__ constexpr int ENC_CONV(int i, int f) { return 1 + i * 6 + f; }
+constexpr int ENC_LSTM_F_W = 19, ENC_LSTM_F_B = 20, ENC_LSTM_B_W = 21, ENC_LSTM_B_B = 22;
+constexpr int DEC_L0_W = 23, DEC_L0_B = 24, DEC_L1_W = 25, DEC_L1_B = 26;
+constexpr int PROJ_W = 27, PROJ_B = 28, PRE1_W = 29, PRE2_W = 30;
+// postnet conv i (0..4): w, b [, bn_scale, bn_offset, bn_mean, bn_var for i<4]
+__host__ __device__ constexpr int POST_CONV(int i, int f) { return 31 + i * 6 + f; }
+constexpr int COUNT = 31 + 4 * 6 + 2;
+}  // namespace aci

@@ -1,0 +1,241 @@
+"""Engine: one libviettts_b200 context per GPU + the host-side plumbing around it.
+
+Host buffers are numpy arrays (the reference's seams take/return numpy / jax
+arrays on the host); device buffers are torch tensors used purely as memory
+containers (`tensor.data_ptr()` is what crosses the C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib, config, weights
+
+DROPOUT_OFF, DROPOUT_MASK, DROPOUT_SEED = 0, 1, 2
+MAX_ACOUSTIC_ROWS = 128   # rows per vtts_acoustic_forward call (csrc/nat.cu MAX_ROWS)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _np(a, dtype, shape=None, what="array"):
+    a = np.ascontiguousarray(np.asarray(a), dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{what}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+class Engine:
+    """A context on one B200.  Not thread-safe (like the C context)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = _lib.c_ctx()
+        rc = self.lib.vtts_create(self.device, C.byref(h))
+        if rc != 0:
+            msg = self.lib.vtts_last_error(None)
+            raise _lib.VttsError(rc, msg.decode() if msg else "?")
+        self.h = h
+        self._hifigan_key = None
+        self._acoustic_key = None
+        self._mel_loaded = False
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vtts_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _lib.check(self.h, rc)
+
+    # ---- info ----
+    def device_info(self) -> dict:
+        sm, ma, mi, hb = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self._ck(self.lib.vtts_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(hb)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), hbm_bytes=hb.value)
+
+    def launch_count(self) -> int:
+        return int(self.lib.vtts_launch_count(self.h))
+
+    def last_stage_ms(self, stage: int) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.vtts_last_stage_ms(self.h, stage, C.byref(ms)))
+        return float(ms.value)
+
+    # ---- weights ----
+    def load_hifigan(self, params, key=None):
+        """params: Haiku-layout dict, a packed float32 numpy blob, or a torch CUDA
+        tensor holding the blob (e.g. received through an NCCL broadcast)."""
+        blob = weights.pack_hifigan(params) if isinstance(params, dict) else params
+        n = int(blob.size if isinstance(blob, np.ndarray) else blob.numel())
+        if isinstance(blob, np.ndarray):
+            blob = _np(blob, np.float32)
+        self._ck(self.lib.vtts_load_hifigan(self.h, _ptr(blob), n))
+        self._hifigan_key = key if key is not None else object()
+
+    def load_acoustic(self, ckpt, key=None):
+        blob = weights.pack_acoustic(ckpt) if isinstance(ckpt, dict) else ckpt
+        n = int(blob.size if isinstance(blob, np.ndarray) else blob.numel())
+        if isinstance(blob, np.ndarray):
+            blob = _np(blob, np.float32)
+        self._ck(self.lib.vtts_load_acoustic(self.h, _ptr(blob), n))
+        self._acoustic_key = key if key is not None else object()
+
+    def load_mel_filterbank(self, fb=None):
+        fb = _np(weights.mel_filterbank() if fb is None else fb, np.float32, (config.MEL_DIM, config.N_FFT // 2 + 1), "filterbank")
+        self._ck(self.lib.vtts_load_mel_filterbank(self.h, _ptr(fb), fb.shape[0], fb.shape[1]))
+        self._mel_loaded = True
+
+    # ---- host-buffer calls -----------------------------------------------------------
+    def mel2wave(self, mel, n_frames=None) -> np.ndarray:
+        """mel f32 [B,T,80] -> wav f32 [B,256T] (Generator.__call__, hifigan/model.py:109-125)."""
+        mel = _np(mel, np.float32)
+        if mel.ndim != 3 or mel.shape[2] != config.MEL_DIM:
+            raise ValueError(f"mel must be [B,T,{config.MEL_DIM}], got {mel.shape}")
+        B, T, _ = mel.shape
+        nf = None if n_frames is None else _np(n_frames, np.int32, (B,), "n_frames")
+        wav = np.empty((B, T * config.HOP), np.float32)
+        self._ck(self.lib.vtts_mel2wave_host(self.h, _ptr(mel), _ptr(nf), B, T, _ptr(wav)))
+        return wav
+
+    def _acoustic_args(self, tokens, dur_frames, lengths, n_frames, masks, seed):
+        tokens = _np(tokens, np.int32)
+        if tokens.ndim != 2:
+            raise ValueError("tokens must be [B,L]")
+        B, L = tokens.shape
+        dur = _np(dur_frames, np.float32, (B, L), "durations")
+        lens = None if lengths is None else _np(lengths, np.int32, (B,), "lengths")
+        if n_frames is None:
+            nf = np.array([int(np.sum(dur[b, : (L if lens is None else lens[b])], dtype=np.float32)) for b in range(B)], np.int32)
+        else:
+            nf = _np(n_frames, np.int32, (B,), "n_frames")
+        N = int(nf.max())
+        if N < 1:
+            raise ValueError("durations sum to less than one frame")
+        if masks is not None:
+            mode = DROPOUT_MASK
+            masks = _np(masks, np.uint8)
+            if masks.shape[0] != B or masks.shape[1] < N or masks.shape[2:] != (2, config.PRENET_DIM):
+                raise ValueError(f"masks must be uint8 [B,>=N,2,256], got {masks.shape}")
+            masks = np.ascontiguousarray(masks[:, :N])
+        elif seed is not None:
+            mode = DROPOUT_SEED
+        else:
+            mode = DROPOUT_OFF
+        return tokens, dur, lens, nf, N, masks, mode, int(seed or 0)
+
+    def predict_mel(self, tokens, dur_frames, lengths=None, n_frames=None, masks=None, seed=None) -> np.ndarray:
+        """AcousticModel.inference for a (ragged) batch: tokens int [B,L], durations in FRAMES
+        [B,L] -> mel f32 [B,N,80] with N = max_b n_frames[b] (rows past n_frames[b] are 0).
+        Dropout (live at inference in the reference): `masks` uint8 [B,N,2,256] keep-masks,
+        else `seed` for the on-device threefry stream, else off."""
+        tokens, dur, lens, nf, N, masks, mode, seed = self._acoustic_args(tokens, dur_frames, lengths, n_frames, masks, seed)
+        B, L = tokens.shape
+        mel = np.empty((B, N, config.MEL_DIM), np.float32)
+        for b0 in range(0, B, MAX_ACOUSTIC_ROWS):
+            b1 = min(B, b0 + MAX_ACOUSTIC_ROWS)
+            sl = slice(b0, b1)
+            out = np.empty((b1 - b0, N, config.MEL_DIM), np.float32)
+            self._ck(self.lib.vtts_predict_mel_host(
+                self.h, _ptr(tokens[sl]), _ptr(None if lens is None else lens[sl]), _ptr(dur[sl]), _ptr(nf[sl]),
+                _ptr(None if masks is None else np.ascontiguousarray(masks[sl])), mode, seed + b0, b1 - b0, L, N, _ptr(out)))
+            mel[sl] = out
+        return mel
+
+    def synthesize(self, tokens, dur_frames, lengths=None, n_frames=None, masks=None, seed=None, return_mel=False):
+        """predict_mel -> mel2wave with the mel staying on the device.  Returns wav [B,256N]
+        (and mel [B,N,80] if return_mel)."""
+        tokens, dur, lens, nf, N, masks, mode, seed = self._acoustic_args(tokens, dur_frames, lengths, n_frames, masks, seed)
+        B, L = tokens.shape
+        wav = np.empty((B, N * config.HOP), np.float32)
+        mel = np.empty((B, N, config.MEL_DIM), np.float32) if return_mel else None
+        for b0 in range(0, B, MAX_ACOUSTIC_ROWS):
+            b1 = min(B, b0 + MAX_ACOUSTIC_ROWS)
+            sl = slice(b0, b1)
+            w = np.empty((b1 - b0, N * config.HOP), np.float32)
+            m = np.empty((b1 - b0, N, config.MEL_DIM), np.float32) if return_mel else None
+            self._ck(self.lib.vtts_synthesize_host(
+                self.h, _ptr(tokens[sl]), _ptr(None if lens is None else lens[sl]), _ptr(dur[sl]), _ptr(nf[sl]),
+                _ptr(None if masks is None else np.ascontiguousarray(masks[sl])), mode, seed + b0, b1 - b0, L, N, _ptr(m), _ptr(w)))
+            wav[sl] = w
+            if return_mel:
+                mel[sl] = m
+        return (wav, mel) if return_mel else wav
+
+    def melspec(self, wav) -> np.ndarray:
+        """MelFilter.__call__ (nat/dsp.py:115-128): wav f32 [B,S] -> log-mel [B,S/256,80]."""
+        if not self._mel_loaded:
+            self.load_mel_filterbank()
+        wav = _np(wav, np.float32)
+        assert wav.ndim == 2, "MelFilter expects [B,S] (dsp.py:118)"
+        B, S = wav.shape
+        mel = np.empty((B, S // config.HOP, config.MEL_DIM), np.float32)
+        self._ck(self.lib.vtts_melspec_host(self.h, _ptr(wav), B, S, _ptr(mel)))
+        return mel
+
+    def debug_read(self, name: str, shape) -> np.ndarray:
+        out = np.empty(shape, np.float32)
+        self._ck(self.lib.vtts_debug_read(self.h, name.encode(), _ptr(out), out.size))
+        return out
+
+    # ---- device-pointer calls (torch tensors as memory containers) --------------------
+    def hifigan_forward(self, mel_t, n_frames_t=None, out=None, stream=None):
+        import torch
+        assert mel_t.is_cuda and mel_t.dtype == torch.float32 and mel_t.is_contiguous()
+        B, T, _ = mel_t.shape
+        if out is None:
+            out = torch.empty((B, T * config.HOP), dtype=torch.float32, device=mel_t.device)
+        st = torch.cuda.current_stream(mel_t.device).cuda_stream if stream is None else stream
+        self._ck(self.lib.vtts_hifigan_forward(self.h, _ptr(mel_t), _ptr(n_frames_t), B, T, _ptr(out), st))
+        return out
+
+    def acoustic_forward(self, tokens_t, dur_t, N, lengths_t=None, n_frames_t=None, masks_t=None, seed=None, out=None, stream=None):
+        import torch
+        assert tokens_t.is_cuda and tokens_t.dtype == torch.int32 and dur_t.dtype == torch.float32
+        B, L = tokens_t.shape
+        if out is None:
+            out = torch.empty((B, N, config.MEL_DIM), dtype=torch.float32, device=tokens_t.device)
+        mode = DROPOUT_MASK if masks_t is not None else (DROPOUT_SEED if seed is not None else DROPOUT_OFF)
+        st = torch.cuda.current_stream(tokens_t.device).cuda_stream if stream is None else stream
+        self._ck(self.lib.vtts_acoustic_forward(self.h, _ptr(tokens_t), _ptr(lengths_t), _ptr(dur_t), _ptr(n_frames_t),
+                                                _ptr(masks_t), mode, int(seed or 0), B, L, int(N), _ptr(out), st))
+        return out
+
+    def melspec_forward(self, wav_t, out=None, stream=None):
+        import torch
+        if not self._mel_loaded:
+            self.load_mel_filterbank()
+        B, S = wav_t.shape
+        if out is None:
+            out = torch.empty((B, S // config.HOP, config.MEL_DIM), dtype=torch.float32, device=wav_t.device)
+        st = torch.cuda.current_stream(wav_t.device).cuda_stream if stream is None else stream
+        self._ck(self.lib.vtts_melspec(self.h, _ptr(wav_t), B, S, _ptr(out), st))
+        return out
+
+
+_engines: dict = {}
+_lock = threading.Lock()
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine per device (LOCAL_RANK by default under torchrun)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _lock:
+        if device not in _engines:
+            _engines[device] = Engine(device)
+        return _engines[device]
