@@ -51,12 +51,21 @@ typedef enum vtts_dropout_mode {
   VTTS_DROPOUT_SEED = 2     /* keep bits drawn on device from threefry2x32(seed; b,t,layer,unit) */
 } vtts_dropout_mode;
 
+/* arithmetic of the dense conv contractions (97 % of the FLOPs):
+ *   FP32    every product and sum in IEEE fp32 on the FMA pipe (conv1d.cu) -- the strict parity mode
+ *   BF16X3  tcgen05 tensor cores, each fp32 operand split into bf16 hi+lo, three products
+ *           (hi*hi + hi*lo + lo*hi) accumulated in fp32 in TMEM (tc_conv.cu); fp32-class accuracy
+ *           (waveform L-inf 2e-5 vs float64), no reduced-precision storage anywhere. */
+typedef enum vtts_precision { VTTS_PRECISION_FP32 = 0, VTTS_PRECISION_BF16X3 = 1 } vtts_precision;
+
 /* ---- library / context ------------------------------------------------------------ */
 int vtts_version(void);                                  /* ABI version, currently 1 */
 int vtts_create(int device, vtts_ctx** out);
 int vtts_destroy(vtts_ctx* ctx);
 const char* vtts_last_error(vtts_ctx* ctx);              /* ctx may be NULL: last error of failed create */
 int vtts_device_info(vtts_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+int vtts_set_precision(vtts_ctx* ctx, int mode);          /* vtts_precision; applies to later forward calls */
+int vtts_get_precision(vtts_ctx* ctx);
 
 /* ---- weights --------------------------------------------------------------------------
  * A "blob" is the float32 concatenation of the Haiku-layout tensors in the canonical order
@@ -95,6 +104,13 @@ int vtts_melspec(vtts_ctx* ctx, const float* wav_dev, int B, int S, float* mel_d
 /* optional taps for tests: copy an internal activation of the LAST forward call to host.
  * name: "enc" [B,L,512], "cond" [B,N,512], "mel_pre" [B,N,80] (before the postnet). */
 int vtts_debug_read(vtts_ctx* ctx, const char* name, float* host_out, int64_t n_floats);
+
+/* test hook: one hk.Conv1D (SAME padding, dilation, optional leaky_relu on the input and residual
+ * add) on device buffers through either arithmetic path.  x [B,T,Cin], w Haiku layout [k,Cin,Cout],
+ * out/resid [B,T,Cout]; len int32 [B] or NULL; pre_slope 1.0 = no input activation.  Synchronous. */
+int vtts_debug_conv1d(vtts_ctx* ctx, int precision, const float* x_dev, const float* w_dev, const float* bias_dev,
+                      const float* resid_dev, const int32_t* len_dev, int B, int T, int Cin, int Cout, int k, int dil,
+                      float pre_slope, float* out_dev);
 
 /* ---- host-buffer entry points (what a ctypes / cgo / JNI binding calls) ------------------ */
 int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav);

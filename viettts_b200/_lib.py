@@ -23,6 +23,10 @@ SIGNATURES = {
     "vtts_destroy": (C.c_int, [c_ctx]),
     "vtts_last_error": (C.c_char_p, [c_ctx]),
     "vtts_device_info": (C.c_int, [c_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "vtts_set_precision": (C.c_int, [c_ctx, C.c_int]),
+    "vtts_get_precision": (C.c_int, [c_ctx]),
+    "vtts_debug_conv1d": (C.c_int, [c_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "vtts_hifigan_blob_floats": (C.c_int64, []),
     "vtts_acoustic_blob_floats": (C.c_int64, []),
     "vtts_load_hifigan": (C.c_int, [c_ctx, C.c_void_p, C.c_int64]),

@@ -216,6 +216,11 @@ int vtts_create(int device, vtts_ctx** out) {
     cudaEventCreate(&ctx->ev0[i]);
     cudaEventCreate(&ctx->ev1[i]);
   }
+  if (cudaMalloc(&ctx->d_err, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_err, 0, sizeof(int)) != cudaSuccess) {
+    g_vtts_create_error = "vtts_create: cannot allocate the error flag";
+    delete ctx;
+    return VTTS_ERR_CUDA;
+  }
   *out = ctx;
   return VTTS_OK;
 }
@@ -226,7 +231,7 @@ int vtts_destroy(vtts_ctx* ctx) {
   cudaDeviceSynchronize();
   cudaFree(ctx->hg_blob); cudaFree(ctx->hg_upsw); cudaFree(ctx->ac_blob); cudaFree(ctx->ac_derived);
   cudaFree(ctx->mel_fb); cudaFree(ctx->mel_lo); cudaFree(ctx->mel_hi); cudaFree(ctx->fft_tw); cudaFree(ctx->hann);
-  cudaFree(ctx->ws); cudaFree(ctx->dstage);
+  cudaFree(ctx->ws); cudaFree(ctx->dstage); cudaFree(ctx->d_err); cudaFree(ctx->hg_wpk);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
   for (int i = 0; i < 3; ++i) {
     cudaEventDestroy(ctx->ev0[i]);
@@ -245,6 +250,50 @@ int vtts_device_info(vtts_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
   if (cc_major) *cc_major = ctx->cc_major;
   if (cc_minor) *cc_minor = ctx->cc_minor;
   if (hbm_bytes) *hbm_bytes = (int64_t)ctx->hbm_bytes;
+  return VTTS_OK;
+}
+
+int vtts_set_precision(vtts_ctx* ctx, int mode) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (mode != VTTS_PRECISION_FP32 && mode != VTTS_PRECISION_BF16X3) return ctx->fail(VTTS_ERR_BAD_ARG, "set_precision: mode %d", mode);
+  ctx->precision = mode;
+  return VTTS_OK;
+}
+
+int vtts_get_precision(vtts_ctx* ctx) { return ctx ? ctx->precision : VTTS_ERR_BAD_ARG; }
+
+int vtts_debug_conv1d(vtts_ctx* ctx, int precision, const float* x_dev, const float* w_dev, const float* bias_dev,
+                      const float* resid_dev, const int32_t* len_dev, int B, int T, int Cin, int Cout, int k, int dil,
+                      float pre_slope, float* out_dev) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  if (precision == VTTS_PRECISION_FP32) {
+    ConvLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.nprob = 1; L.Cin = Cin; L.Cout = Cout; L.B = B; L.T_rows = T; L.rows_out = T; L.len = len_dev; L.len_mul = 1;
+    L.pre_mode = pre_slope == 1.0f ? 0 : 1; L.pre_slope = pre_slope; L.post_act = 0;
+    L.p[0] = ConvProb{x_dev, nullptr, nullptr, w_dev, bias_dev, resid_dev, nullptr, nullptr, nullptr, out_dev, k, dil, -((k - 1) * dil) / 2, 1, 0};
+    int rc = vtts_launch_conv(ctx, L, nullptr);
+    if (rc) return rc;
+  } else {
+    void* wpk = nullptr;
+    VTTS_CUDA(cudaMalloc(&wpk, vtts_tc_packed_elems(k, Cin, Cout) * 2));
+    int rc = vtts_tc_pack_weights(ctx, w_dev, wpk, k, Cin, Cout, 0, Cout);
+    if (rc) { cudaFree(wpk); return rc; }
+    TcLaunch TL;
+    memset(&TL, 0, sizeof(TL));
+    TL.nprob = 1; TL.Cin = Cin; TL.N = Cout; TL.in_ld = Cin; TL.out_ld = Cout; TL.B = B; TL.T_rows = T; TL.rows_out = T;
+    TL.len = len_dev; TL.len_mul = 1; TL.pre_mode = pre_slope == 1.0f ? 0 : 1; TL.pre_slope = pre_slope;
+    TL.p[0] = TcProb{x_dev, nullptr, nullptr, wpk, bias_dev, resid_dev, out_dev, k, dil, -((k - 1) * dil) / 2, 1, 0};
+    rc = vtts_launch_tc_conv(ctx, TL, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(wpk);
+    if (rc) return rc;
+    if (e != cudaSuccess) {
+      return ctx->fail(VTTS_ERR_CUDA, "debug_conv1d (tensor path): %s", cudaGetErrorString(e));
+    }
+  }
+  VTTS_CUDA(cudaDeviceSynchronize());
   return VTTS_OK;
 }
 

@@ -128,6 +128,31 @@ int vtts_hifigan_prepare(vtts_ctx* ctx) {
     VTTS_CUDA(cudaGetLastError());
     C /= 2;
   }
+  // ---- tensor-core path: bf16 hi/lo split + canonical K-major packing of the 72 resblock convs ----
+  {
+    size_t elems = 0;
+    std::vector<size_t> eoff(72);
+    for (int n = 0; n < 12; ++n) {
+      const int ch = 256 >> (n / 3), kk = vc::hg_rbk(n % 3);
+      for (int q = 0; q < 6; ++q) {
+        eoff[n * 6 + q] = elems;
+        elems += vtts_tc_packed_elems(kk, ch, ch);
+      }
+    }
+    if (ctx->hg_wpk) cudaFree(ctx->hg_wpk);
+    VTTS_CUDA(cudaMalloc(&ctx->hg_wpk, elems * 2));
+    ctx->hg_wpk_t.resize(72);
+    for (int n = 0; n < 12; ++n) {
+      const int ch = 256 >> (n / 3), kk = vc::hg_rbk(n % 3);
+      for (int which = 0; which < 2; ++which)
+        for (int m = 0; m < 3; ++m) {
+          const int q = which * 3 + m;
+          ctx->hg_wpk_t[n * 6 + q] = (char*)ctx->hg_wpk + eoff[n * 6 + q] * 2;
+          int rc = vtts_tc_pack_weights(ctx, ctx->hg_t[hgi::RB_W(n, which, m)], ctx->hg_wpk_t[n * 6 + q], kk, ch, ch, 0, ch);
+          if (rc) return rc;
+        }
+    }
+  }
   VTTS_CUDA(cudaDeviceSynchronize());
   return VTTS_OK;
 }
@@ -193,15 +218,41 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
     const int scale = scale_in * u;
     for (int m = 0; m < 3; ++m) {
       const int d = vc::hg_dil(m);
+      const float* src[3];
+      for (int j = 0; j < 3; ++j) src[j] = (m == 0) ? hb.X : (m == 1 ? hb.A[par][j] : hb.Bb[j]);
+      if (ctx->precision == 1) {
+        // ---- bf16x3 tensor-core path (tc_conv.cu) ----
+        TcLaunch TL;
+        for (int which = 0; which < 2; ++which) {
+          memset(&TL, 0, sizeof(TL));
+          TL.nprob = 3; TL.Cin = Co; TL.N = Co; TL.in_ld = Co; TL.out_ld = Co;
+          TL.B = B; TL.T_rows = rows; TL.rows_out = rows; TL.len = n_frames; TL.len_mul = scale;
+          TL.pre_mode = 1; TL.pre_slope = 0.1f;
+          for (int j = 0; j < 3; ++j) {
+            const int kk = vc::hg_rbk(j), n = i * 3 + j;
+            const int dd = which == 0 ? d : 1;
+            TcProb p;
+            memset(&p, 0, sizeof(p));
+            p.x0 = which == 0 ? src[j] : hb.Tb[j];
+            p.wpk = ctx->hg_wpk_t[n * 6 + which * 3 + m];
+            p.bias = W[hgi::RB_B(n, which, m)];
+            p.resid = which == 0 ? nullptr : src[j];
+            p.out = which == 0 ? hb.Tb[j] : ((m == 1) ? hb.Bb[j] : hb.A[par][j]);
+            p.k = kk; p.dil = dd; p.in_off = -((kk - 1) * dd) / 2; p.out_stride = 1; p.out_off = 0;
+            TL.p[j] = p;
+          }
+          rc = vtts_launch_tc_conv(ctx, TL, st);
+          if (rc) return rc;
+        }
+        continue;
+      }
       // conv1 (dilated)
       memset(&L, 0, sizeof(L));
       L.B = B; L.len = n_frames; L.len_mul = scale;
       L.nprob = 3; L.Cin = Co; L.Cout = Co; L.T_rows = rows; L.rows_out = rows;
       L.pre_mode = 1; L.pre_slope = 0.1f; L.post_act = 0;
-      const float* src[3];
       for (int j = 0; j < 3; ++j) {
         const int kk = vc::hg_rbk(j), n = i * 3 + j;
-        src[j] = (m == 0) ? hb.X : (m == 1 ? hb.A[par][j] : hb.Bb[j]);
         ConvProb p;
         memset(&p, 0, sizeof(p));
         p.x0 = src[j];

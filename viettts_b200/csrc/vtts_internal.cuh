@@ -68,8 +68,38 @@ struct ConvLaunch {
   int post_act;       // 0 none, 1 tanh, 2 relu
 };
 
+// ---- tensor-core conv (tc_conv.cu) ----------------------------------------------------------------
+struct TcProb {
+  const float* x0;
+  const float* x1;
+  const float* x2;
+  const void* wpk;       // packed bf16 hi/lo weights (vtts_tc_pack_weights)
+  const float* bias;     // [N]
+  const float* resid;    // rows_out x out_ld or null
+  float* out;
+  int k, dil, in_off, out_stride, out_off;
+};
+
+struct TcLaunch {
+  TcProb p[3];
+  int nprob;
+  int Cin, N;            // N = output channels of this launch (32/64/128/256)
+  int in_ld, out_ld;     // row strides in floats
+  int B, T_rows, rows_out;
+  const int* len;
+  int len_mul;
+  int pre_mode;
+  float pre_slope;
+  int tiles_per_row, ntiles;  // filled by the launcher
+  int* err;                   // device int: set before trapping on a barrier timeout
+};
+
 struct vtts_ctx {
   int device = 0;
+  int precision = 0;            // 0 = strict fp32 (FMA pipe), 1 = bf16x3 on tcgen05 tensor cores
+  int* d_err = nullptr;
+  void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
+  std::vector<void*> hg_wpk_t;
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   size_t hbm_bytes = 0;
@@ -141,6 +171,10 @@ struct Arena {
 
 // conv1d.cu
 int vtts_launch_conv(vtts_ctx* ctx, const ConvLaunch& L, cudaStream_t st);
+// tc_conv.cu
+size_t vtts_tc_packed_elems(int k, int Cin, int N);
+int vtts_tc_pack_weights(vtts_ctx* ctx, const float* w, void* dst, int k, int Cin, int Cout_total, int n0, int N);
+int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st);
 // hifigan.cu
 int vtts_hifigan_prepare(vtts_ctx* ctx);   // derived weights after load
 int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav, cudaStream_t st);

@@ -13,6 +13,7 @@ import numpy as np
 from . import _lib, config, weights
 
 DROPOUT_OFF, DROPOUT_MASK, DROPOUT_SEED = 0, 1, 2
+PRECISION_FP32, PRECISION_BF16X3 = 0, 1
 MAX_ACOUSTIC_ROWS = 128   # rows per vtts_acoustic_forward call (csrc/nat.cu MAX_ROWS)
 
 
@@ -74,6 +75,22 @@ class Engine:
         ms = C.c_float()
         self._ck(self.lib.vtts_last_stage_ms(self.h, stage, C.byref(ms)))
         return float(ms.value)
+
+    def set_precision(self, mode) -> None:
+        """'fp32' (strict, FMA pipe) or 'bf16x3' (tcgen05 tensor cores, split-bf16, fp32 accumulate)."""
+        m = {"fp32": PRECISION_FP32, "bf16x3": PRECISION_BF16X3}.get(mode, mode)
+        self._ck(self.lib.vtts_set_precision(self.h, int(m)))
+
+    def debug_conv1d(self, precision, x_t, w_t, bias_t, k, dil, pre_slope=1.0, resid_t=None, len_t=None):
+        """Test hook: one conv layer on torch CUDA tensors through either arithmetic path."""
+        import torch
+        B, T, Cin = x_t.shape
+        Cout = w_t.shape[2]
+        out = torch.empty((B, T, Cout), dtype=torch.float32, device=x_t.device)
+        m = {"fp32": PRECISION_FP32, "bf16x3": PRECISION_BF16X3}.get(precision, precision)
+        self._ck(self.lib.vtts_debug_conv1d(self.h, int(m), _ptr(x_t), _ptr(w_t), _ptr(bias_t), _ptr(resid_t), _ptr(len_t),
+                                            B, T, Cin, Cout, int(k), int(dil), float(pre_slope), _ptr(out)))
+        return out
 
     # ---- weights ----
     def load_hifigan(self, params, key=None):
