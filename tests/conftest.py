@@ -10,6 +10,11 @@ if str(REPO) not in sys.path:
 
 
 def pytest_configure(config):
+    try:  # the CPU oracle is small-op bound: 128 threads on a big host only add overhead
+        import torch
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 

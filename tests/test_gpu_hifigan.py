@@ -19,6 +19,7 @@ def eng(hifigan_params):
     from viettts_b200.engine import Engine
     e = Engine(0)
     e.load_hifigan(hifigan_params)
+    e.set_precision("fp32")      # this file checks the strict fp32 path; test_gpu_tc_conv.py the bf16x3 one
     yield e
     e.close()
 

@@ -128,10 +128,11 @@ int vtts_hifigan_prepare(vtts_ctx* ctx) {
     VTTS_CUDA(cudaGetLastError());
     C /= 2;
   }
-  // ---- tensor-core path: bf16 hi/lo split + canonical K-major packing of the 72 resblock convs ----
+  // ---- tensor-core path: bf16 hi/lo split + canonical K-major packing of every dense conv ----
   {
+    VTTS_CUDA(cudaDeviceSynchronize());  // hg_upsw must be complete: the phase weights are packed from it
     size_t elems = 0;
-    std::vector<size_t> eoff(72);
+    std::vector<size_t> eoff(72), uoff(32), poff(2);
     for (int n = 0; n < 12; ++n) {
       const int ch = 256 >> (n / 3), kk = vc::hg_rbk(n % 3);
       for (int q = 0; q < 6; ++q) {
@@ -139,9 +140,22 @@ int vtts_hifigan_prepare(vtts_ctx* ctx) {
         elems += vtts_tc_packed_elems(kk, ch, ch);
       }
     }
+    int Cc = vc::HG_C0;
+    for (int i = 0; i < 4; ++i) {
+      for (int r = 0; r < vc::hg_rate(i); ++r) {
+        uoff[i * 8 + r] = elems;
+        elems += vtts_tc_packed_elems(2, Cc, Cc / 2);
+      }
+      Cc /= 2;
+    }
+    for (int t = 0; t < 2; ++t) {
+      poff[t] = elems;
+      elems += vtts_tc_packed_elems(7, vc::MEL, 256);
+    }
     if (ctx->hg_wpk) cudaFree(ctx->hg_wpk);
     VTTS_CUDA(cudaMalloc(&ctx->hg_wpk, elems * 2));
     ctx->hg_wpk_t.resize(72);
+    ctx->hg_wpk_ups.assign(32, nullptr);
     for (int n = 0; n < 12; ++n) {
       const int ch = 256 >> (n / 3), kk = vc::hg_rbk(n % 3);
       for (int which = 0; which < 2; ++which)
@@ -151,6 +165,21 @@ int vtts_hifigan_prepare(vtts_ctx* ctx) {
           int rc = vtts_tc_pack_weights(ctx, ctx->hg_t[hgi::RB_W(n, which, m)], ctx->hg_wpk_t[n * 6 + q], kk, ch, ch, 0, ch);
           if (rc) return rc;
         }
+    }
+    Cc = vc::HG_C0;
+    for (int i = 0; i < 4; ++i) {
+      const int Co = Cc / 2;
+      for (int r = 0; r < vc::hg_rate(i); ++r) {
+        ctx->hg_wpk_ups[i * 8 + r] = (char*)ctx->hg_wpk + uoff[i * 8 + r] * 2;
+        int rc = vtts_tc_pack_weights(ctx, ctx->hg_upsw + offs[i] + (size_t)r * 2 * Cc * Co, ctx->hg_wpk_ups[i * 8 + r], 2, Cc, Co, 0, Co);
+        if (rc) return rc;
+      }
+      Cc = Co;
+    }
+    for (int t = 0; t < 2; ++t) {
+      ctx->hg_wpk_pre[t] = (char*)ctx->hg_wpk + poff[t] * 2;
+      int rc = vtts_tc_pack_weights(ctx, ctx->hg_t[hgi::PRE_W], ctx->hg_wpk_pre[t], 7, vc::MEL, vc::HG_C0, 256 * t, 256);
+      if (rc) return rc;
     }
   }
   VTTS_CUDA(cudaDeviceSynchronize());
@@ -180,7 +209,18 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
   L.T_rows = T; L.rows_out = T; L.len_mul = 1;
   L.pre_mode = 0; L.pre_slope = 1.f; L.post_act = 0;
   L.p[0] = ConvProb{mel, nullptr, nullptr, W[hgi::PRE_W], W[hgi::PRE_B], nullptr, nullptr, nullptr, nullptr, hb.P0, 7, 1, -3, 1, 0};
-  rc = vtts_launch_conv(ctx, L, st);
+  const bool tc = ctx->precision == 1;
+  if (tc) {
+    TcLaunch TL;
+    memset(&TL, 0, sizeof(TL));
+    TL.nprob = 2; TL.Cin = vc::MEL; TL.N = 256; TL.in_ld = vc::MEL; TL.out_ld = vc::HG_C0;
+    TL.B = B; TL.T_rows = T; TL.rows_out = T; TL.len = n_frames; TL.len_mul = 1; TL.pre_mode = 0; TL.pre_slope = 1.f;
+    for (int t = 0; t < 2; ++t)
+      TL.p[t] = TcProb{mel, nullptr, nullptr, ctx->hg_wpk_pre[t], W[hgi::PRE_B] + 256 * t, nullptr, hb.P0 + 256 * t, 7, 1, -3, 1, 0};
+    rc = vtts_launch_tc_conv(ctx, TL, st);
+  } else {
+    rc = vtts_launch_conv(ctx, L, st);
+  }
   if (rc) return rc;
 
   int C = vc::HG_C0;      // input channels of the stage
@@ -209,7 +249,20 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
       p.k = 2; p.dil = 1; p.in_off = e; p.out_stride = u; p.out_off = r;
       L.p[r] = p;
     }
-    rc = vtts_launch_conv(ctx, L, st);
+    if (tc) {
+      TcLaunch TL;
+      memset(&TL, 0, sizeof(TL));
+      TL.nprob = u; TL.Cin = C; TL.N = Co; TL.in_ld = C; TL.out_ld = Co;
+      TL.B = B; TL.T_rows = rows_in; TL.rows_out = rows_in * u; TL.len = n_frames; TL.len_mul = scale_in;
+      TL.pre_mode = L.pre_mode; TL.pre_slope = 0.1f;
+      for (int r = 0; r < u; ++r) {
+        const ConvProb& cp = L.p[r];
+        TL.p[r] = TcProb{cp.x0, cp.x1, cp.x2, ctx->hg_wpk_ups[i * 8 + r], cp.bias, nullptr, cp.out, 2, 1, cp.in_off, u, r};
+      }
+      rc = vtts_launch_tc_conv(ctx, TL, st);
+    } else {
+      rc = vtts_launch_conv(ctx, L, st);
+    }
     if (rc) return rc;
     ups_off += (size_t)u * 2 * C * Co;
 
@@ -220,7 +273,7 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
       const int d = vc::hg_dil(m);
       const float* src[3];
       for (int j = 0; j < 3; ++j) src[j] = (m == 0) ? hb.X : (m == 1 ? hb.A[par][j] : hb.Bb[j]);
-      if (ctx->precision == 1) {
+      if (tc) {
         // ---- bf16x3 tensor-core path (tc_conv.cu) ----
         TcLaunch TL;
         for (int which = 0; which < 2; ++which) {

@@ -340,14 +340,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) enc_scan_kernel(const EncScan
 }
 
 // ---- autoregressive decoder scan (model.py:129-142) ------------------------------------------------
+// Per frame t (B rows at once), four grid-wide phases:
+//   EA  p1(t) = drop(relu(mel_{t-1} . W1))  computed as relu([h0,h1]_{t-1} . (Wo.W1) + bo.W1)  (2 cols / CTA)
+//       and mel_{t-1} = [h0,h1]_{t-1} . Wo + bo  (the output frame, CTAs 0..79)
+//   B   p2(t) = drop(relu(p1 . W2))                                                        (2 cols / CTA)
+//   C   LSTM0: z = zc0[t] + [p2, h0_{t-1}] . W0r ; gates -> h0_t                             (4 units / CTA)
+//   D   LSTM1: z = zc1[t] + [p2, h0_t, h1_{t-1}] . W1r ; gates -> h1_t
+// The CTA's slices of the recurrent matrices (768x16 and 1280x16 fp32 = 128 KB) live in REGISTERS:
+// thread (ks, cg) owns K-slice ks (12 / 20 rows) x 4 gate columns of both layers, so shared memory is
+// free to hold the input vectors of all 32 batch rows and each phase costs a single L2 round trip.
 struct DecScanArgs {
   const float* zc0;      // [B][N][2048] cond.W0[0:512] + b0
   const float* zc1;      // [B][N][2048] cond.W1[0:512] + b1
   const float* w0r;      // [128][768][16]   rows 512..1279 of lstm0   ([p2, h0])
   const float* w1r;      // [128][1280][16]  rows 512..1791 of lstm1   ([p2, h0, h1])
-  const float* wp1;      // [128][80][2]     prenet fc1 columns
+  const float* wc;       // [32][1024][8]    (Wo . W1) columns, 8 per EA CTA
+  const float* bc;       // [256]            bo . W1
   const float* wp2;      // [128][256][2]    prenet fc2 columns
-  const float* wo;       // [80][1024]       projection columns
+  const float* wo;       // [20][1024][4]    projection columns, 4 per EA CTA
   const float* bo;       // [80]
   const uint8_t* keep;   // [B][N][2][256] or null
   uint64_t seed;
@@ -356,66 +366,230 @@ struct DecScanArgs {
   float* p2;             // [B][256]
   float* h0;             // [2][B][512]
   float* h1;             // [2][B][512]
-  float* mel;            // [B][N][80]  (pre-postnet output, also the recurrent input)
+  float* mel;            // [B][N][80]  (pre-postnet output)
   int B, N;
-  int row_base;          // first batch row of this launch inside the full batch (mask / seed indexing)
-  int B_total;
 };
+
+constexpr int DEC_XR = 32;                 // batch rows staged at once
+constexpr int DEC_KPAD = vc::PRENET + 2 * vc::DEC_H + 4;   // 1284
+
+// stage rows [row0,row0+nr) of up to 3 concatenated segments into xs[r][DEC_KPAD]
+__device__ __forceinline__ void dec_stage(float* xs, const Seg* segs, int nseg, int row0, int nr) {
+  int koff = 0;
+  for (int s = 0; s < nseg; ++s) {
+    const int n4 = segs[s].n >> 2;
+    const int total = nr * n4;
+    const float* p = segs[s].p;
+    const int stride = segs[s].stride;
+    for (int e0 = threadIdx.x; e0 < total; e0 += SCAN_THREADS * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * SCAN_THREADS;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < total && p) {
+          const int r = e / n4, i4 = (e - r * n4) * 4;
+          v[u] = __ldcg(reinterpret_cast<const float4*>(p + (size_t)(row0 + r) * stride + i4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * SCAN_THREADS;
+        if (e < total) {
+          const int r = e / n4, i4 = (e - r * n4) * 4;
+          *reinterpret_cast<float4*>(xs + (size_t)r * DEC_KPAD + koff + i4) = v[u];
+        }
+      }
+    }
+    koff += segs[s].n;
+  }
+}
+
+// acc[8 rows][4 cols] partial sums over this thread's K slice -> butterfly over the 8 slices of the
+// warp (28 shuffles); afterwards the thread holds the warp-level sums of row (lane>>2), cols cg*4..+3.
+__device__ __forceinline__ float4 warp_reduce_rows(float (&acc)[RG][4], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float a4[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float send = b4 ? acc[r][c] : acc[r + 4][c];
+      const float keep = b4 ? acc[r + 4][c] : acc[r][c];
+      a4[r][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  float a2[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float send = b3 ? a4[r][c] : a4[r + 2][c];
+      const float keep = b3 ? a4[r + 2][c] : a4[r][c];
+      a2[r][c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  float a1[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float send = b2 ? a2[0][c] : a2[1][c];
+    const float keep = b2 ? a2[1][c] : a2[0][c];
+    a1[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  return make_float4(a1[0], a1[1], a1[2], a1[3]);
+}
+
+// one LSTM layer for up to DEC_XR staged rows: z partials -> part[warp][row][16] -> zs[row][16]
+template <int SL>
+__device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, int koff_unused, const float (&w)[SL][4], int ngroups,
+                                           float* part, float* zs) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ks = tid >> 2;
+  for (int g = 0; g < ngroups; ++g) {
+    float acc[RG][4];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    const float* xk = xs + (size_t)(g * RG) * DEC_KPAD + ks * SL;
+#pragma unroll
+    for (int kk = 0; kk < SL; kk += 4) {
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)r * DEC_KPAD + kk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[r][c] = fmaf(xv.x, w[kk + 0][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.y, w[kk + 1][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.z, w[kk + 2][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.w, w[kk + 3][c], acc[r][c]);
+        }
+      }
+    }
+    const float4 s = warp_reduce_rows(acc, lane);
+    // row (lane>>2) of group g, columns (lane&3)*4..+3
+    *reinterpret_cast<float4*>(part + ((size_t)warp * DEC_XR + g * RG + (lane >> 2)) * NCOL + (lane & 3) * 4) = s;
+  }
+  __syncthreads();
+  for (int o = tid; o < ngroups * RG * NCOL; o += SCAN_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < SCAN_THREADS / 32; ++wv) s += part[(size_t)wv * DEC_XR * NCOL + o];
+    zs[o] = s;
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const DecScanArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float sm[];
-  constexpr int H = vc::DEC_H, K0 = vc::PRENET + H, K1 = vc::PRENET + 2 * H, Kpad = K1 + 4;
-  float* w0 = sm;                                   // [(K0+64)][16]
-  float* w1 = w0 + (K0 + NSLICE) * NCOL;            // [(K1+64)][16]
-  float* xs = w1 + (K1 + NSLICE) * NCOL;            // [RG][Kpad]
-  float* part = xs + RG * Kpad;                     // [8][RG*16]
-  float* zs = part + 8 * RG * NCOL;                 // [RG*16]
-  float* cst = zs + RG * NCOL;                      // [2][MAX_ROWS][UPC]
-  float* wp1 = cst + 2 * MAX_ROWS * UPC;            // [80][2]
-  float* wp2 = wp1 + vc::MEL * 2;                   // [256][2]
-  float* wo = wp2 + vc::PRENET * 2;                 // [1024]
+  constexpr int H = vc::DEC_H, K0 = vc::PRENET + H, K1 = vc::PRENET + 2 * H;
+  constexpr int SL0 = K0 / NSLICE, SL1 = K1 / NSLICE;   // 12, 20
+  float* xs = sm;                                   // [DEC_XR][DEC_KPAD]
+  float* part = xs + DEC_XR * DEC_KPAD;             // [8][DEC_XR][16]
+  float* zs = part + 8 * DEC_XR * NCOL;             // [DEC_XR][16]
+  float* cst = zs + DEC_XR * NCOL;                  // [2][MAX_ROWS][UPC]
+  float* wea = cst + 2 * MAX_ROWS * UPC;            // [1024][8]: CTAs 0..31 (Wo.W1) cols 8c..8c+7; CTAs 32..51 Wo cols 4(c-32)..+3 ([1024][4])
+  float* wp2 = wea + 2 * H * 8;                     // [256][2]
   const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ks = tid >> 2, cgp = tid & 3;
   const int B = a.B, N = a.N;
-  load_w16(w0, a.w0r + (size_t)c * K0 * NCOL, K0);
-  load_w16(w1, a.w1r + (size_t)c * K1 * NCOL, K1);
+
+  // ---- register-resident recurrent weight slices ----
+  float w0[SL0][4], w1[SL1][4];
+  {
+    const float* g0 = a.w0r + ((size_t)c * K0 + ks * SL0) * NCOL + cgp * 4;
+#pragma unroll
+    for (int i = 0; i < SL0; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g0 + (size_t)i * NCOL));
+      w0[i][0] = v.x; w0[i][1] = v.y; w0[i][2] = v.z; w0[i][3] = v.w;
+    }
+    const float* g1 = a.w1r + ((size_t)c * K1 + ks * SL1) * NCOL + cgp * 4;
+#pragma unroll
+    for (int i = 0; i < SL1; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g1 + (size_t)i * NCOL));
+      w1[i][0] = v.x; w1[i][1] = v.y; w1[i][2] = v.z; w1[i][3] = v.w;
+    }
+  }
   for (int e = tid; e < 2 * MAX_ROWS * UPC; e += SCAN_THREADS) cst[e] = 0.f;
-  for (int e = tid; e < vc::MEL * 2; e += SCAN_THREADS) wp1[e] = a.wp1[(size_t)c * vc::MEL * 2 + e];
+  constexpr int EA_P1 = 32, EA_MEL = 20;            // CTAs computing p1 (8 cols each) / mel (4 cols each)
+  if (c < EA_P1)
+    for (int e = tid; e < 2 * H * 8; e += SCAN_THREADS) wea[e] = a.wc[(size_t)c * 2 * H * 8 + e];
+  else if (c < EA_P1 + EA_MEL)
+    for (int e = tid; e < 2 * H * 4; e += SCAN_THREADS) wea[e] = a.wo[(size_t)(c - EA_P1) * 2 * H * 4 + e];
   for (int e = tid; e < vc::PRENET * 2; e += SCAN_THREADS) wp2[e] = a.wp2[(size_t)c * vc::PRENET * 2 + e];
-  if (c < vc::MEL)
-    for (int e = tid; e < 2 * H; e += SCAN_THREADS) wo[e] = a.wo[(size_t)c * 2 * H + e];
-  const float bo = c < vc::MEL ? a.bo[c] : 0.f;
   __syncthreads();
 
-  for (int t = 0; t < N; ++t) {
+  for (int t = 0; t <= N; ++t) {
     const int cur = t & 1, prv = cur ^ 1;
-    // ---- phase A: p1 = dropout(relu(mel_{t-1} . W1)) : 2 outputs per CTA ----
-    for (int b = warp; b < B; b += SCAN_THREADS / 32) {
-      float s0 = 0.f, s1 = 0.f;
-      if (t > 0) {
-        const float* m = a.mel + ((size_t)b * N + (t - 1)) * vc::MEL;
-        for (int i = lane; i < vc::MEL; i += 32) {
-          const float x = __ldcg(m + i);
-          s0 = fmaf(x, wp1[i * 2 + 0], s0);
-          s1 = fmaf(x, wp1[i * 2 + 1], s1);
-        }
+    // ---- phase EA: mel_{t-1} (CTAs 32..51, 4 cols each) and p1(t) (CTAs 0..31, 8 cols each) from [h0,h1]_{t-1} ----
+    if (t > 0 && c < EA_P1 + EA_MEL) {
+      const bool is_p1 = c < EA_P1;
+      for (int row0 = 0; row0 < B; row0 += DEC_XR) {
+        const int nr = min(DEC_XR, B - row0);
+        Seg segs[2];
+        segs[0] = Seg{a.h0 + (size_t)prv * B * H, H, H};
+        segs[1] = Seg{a.h1 + (size_t)prv * B * H, H, H};
+        dec_stage(xs, segs, 2, row0, nr);
+        __syncthreads();
+        for (int r = warp; r < nr; r += SCAN_THREADS / 32) {
+          const float* x = xs + (size_t)r * DEC_KPAD;
+          const int b = row0 + r;
+          if (is_p1) {
+            float s[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            for (int q = 0; q < 8; ++q) s[q] = 0.f;
+#pragma unroll 4
+            for (int i = lane; i < 2 * H; i += 32) {
+              const float xv = x[i];
+              const float4 wa = *reinterpret_cast<const float4*>(wea + i * 8);
+              const float4 wb = *reinterpret_cast<const float4*>(wea + i * 8 + 4);
+              s[0] = fmaf(xv, wa.x, s[0]); s[1] = fmaf(xv, wa.y, s[1]); s[2] = fmaf(xv, wa.z, s[2]); s[3] = fmaf(xv, wa.w, s[3]);
+              s[4] = fmaf(xv, wb.x, s[4]); s[5] = fmaf(xv, wb.y, s[5]); s[6] = fmaf(xv, wb.z, s[6]); s[7] = fmaf(xv, wb.w, s[7]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+            }
+            if (lane < 8 && t < N) {
+              float v = s[0];
+#pragma unroll
+              for (int q = 1; q < 8; ++q) v = lane == q ? s[q] : v;
+              const int u = c * 8 + lane;
+              v = fmaxf(v + __ldg(a.bc + u), 0.f);
+              a.p1[(size_t)b * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, b, t, N, 0, u);
+            }
+          } else {
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int i = lane; i < 2 * H; i += 32) {
+              const float xv = x[i];
+              const float4 wa = *reinterpret_cast<const float4*>(wea + i * 4);
+              s[0] = fmaf(xv, wa.x, s[0]); s[1] = fmaf(xv, wa.y, s[1]); s[2] = fmaf(xv, wa.z, s[2]); s[3] = fmaf(xv, wa.w, s[3]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+            }
+            if (lane < 4) {
+              float v = s[0];
+#pragma unroll
+              for (int q = 1; q < 4; ++q) v = lane == q ? s[q] : v;
+              const int m = (c - EA_P1) * 4 + lane;
+              a.mel[((size_t)b * N + (t - 1)) * vc::MEL + m] = v + __ldg(a.bo + m);
+            }
+          }
         }
+        __syncthreads();
       }
-      if (lane < 2) {
-        const float v = fmaxf(lane == 0 ? s0 : s1, 0.f);
-        const int u = c * 2 + lane;
-        a.p1[(size_t)b * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + b, t, N, 0, u);
-      }
+    } else if (t == 0) {
+      for (int e = tid; e < B * 2; e += SCAN_THREADS) a.p1[(size_t)(e >> 1) * vc::PRENET + c * 2 + (e & 1)] = 0.f;  // prenet(0) = 0
     }
+    if (t == N) break;
     grid.sync();
     // ---- phase B: p2 = dropout(relu(p1 . W2)) ----
     for (int b = warp; b < B; b += SCAN_THREADS / 32) {
       float s0 = 0.f, s1 = 0.f;
       const float* p = a.p1 + (size_t)b * vc::PRENET;
+#pragma unroll
       for (int i = lane; i < vc::PRENET; i += 32) {
         const float x = __ldcg(p + i);
         s0 = fmaf(x, wp2[i * 2 + 0], s0);
@@ -429,19 +603,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       if (lane < 2) {
         const float v = fmaxf(lane == 0 ? s0 : s1, 0.f);
         const int u = c * 2 + lane;
-        a.p2[(size_t)b * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + b, t, N, 1, u);
+        a.p2[(size_t)b * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, b, t, N, 1, u);
       }
     }
     grid.sync();
     // ---- phase C: LSTM0 on [cond_t (hoisted), p2, h0_prev] ----
-    for (int row0 = 0; row0 < B; row0 += RG) {
-      const int nr = min(RG, B - row0);
+    for (int row0 = 0; row0 < B; row0 += DEC_XR) {
+      const int nr = min(DEC_XR, B - row0);
       Seg segs[2];
       segs[0] = Seg{a.p2, vc::PRENET, vc::PRENET};
       segs[1] = Seg{t == 0 ? nullptr : a.h0 + (size_t)prv * B * H, H, H};
-      stage_rows(xs, Kpad, segs, 2, row0, nr, nullptr);
+      dec_stage(xs, segs, 2, row0, nr);
       __syncthreads();
-      matmul16(xs, Kpad, w0, K0, part, zs);
+      dec_matmul<SL0>(xs, 0, w0, (nr + RG - 1) / RG, part, zs);
       if (tid < nr * UPC) {
         const int r = tid / UPC, uu = tid % UPC, b = row0 + r;
         const float* zc = a.zc0 + ((size_t)b * N + t) * (4 * H) + c * UPC + uu;
@@ -454,15 +628,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
     }
     grid.sync();
     // ---- phase D: LSTM1 on [cond_t (hoisted), p2, h0_t, h1_prev] ----
-    for (int row0 = 0; row0 < B; row0 += RG) {
-      const int nr = min(RG, B - row0);
+    for (int row0 = 0; row0 < B; row0 += DEC_XR) {
+      const int nr = min(DEC_XR, B - row0);
       Seg segs[3];
       segs[0] = Seg{a.p2, vc::PRENET, vc::PRENET};
       segs[1] = Seg{a.h0 + (size_t)cur * B * H, H, H};
       segs[2] = Seg{t == 0 ? nullptr : a.h1 + (size_t)prv * B * H, H, H};
-      stage_rows(xs, Kpad, segs, 3, row0, nr, nullptr);
+      dec_stage(xs, segs, 3, row0, nr);
       __syncthreads();
-      matmul16(xs, Kpad, w1, K1, part, zs);
+      dec_matmul<SL1>(xs, 0, w1, (nr + RG - 1) / RG, part, zs);
       if (tid < nr * UPC) {
         const int r = tid / UPC, uu = tid % UPC, b = row0 + r;
         const float* zc = a.zc1 + ((size_t)b * N + t) * (4 * H) + c * UPC + uu;
@@ -474,20 +648,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       __syncthreads();
     }
     grid.sync();
-    // ---- phase E: mel_t[c] = [h0_t, h1_t] . Wo[:, c] + bo[c]  (CTAs 0..79) ----
-    if (c < vc::MEL) {
-      for (int b = warp; b < B; b += SCAN_THREADS / 32) {
-        float s = 0.f;
-        const float* hh0 = a.h0 + ((size_t)cur * B + b) * H;
-        const float* hh1 = a.h1 + ((size_t)cur * B + b) * H;
-        for (int i = lane; i < H; i += 32) s = fmaf(__ldcg(hh0 + i), wo[i], s);
-        for (int i = lane; i < H; i += 32) s = fmaf(__ldcg(hh1 + i), wo[H + i], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) a.mel[((size_t)b * N + t) * vc::MEL + c] = s + bo;
-      }
-    }
-    grid.sync();
+  }
+}
+
+// Wc[i][o] = sum_m Wo[i][m] * W1[m][o]   (1024 x 80) . (80 x 256), double accumulation; bc = bo . W1
+__global__ void precompose_kernel(const float* __restrict__ wo, const float* __restrict__ bo, const float* __restrict__ w1,
+                                  float* __restrict__ wc, float* __restrict__ bc) {
+  const int o = threadIdx.x;            // 256
+  const int i = blockIdx.x;             // 0..1024 (last block computes bc)
+  double s = 0.0;
+  if (i < 2 * vc::DEC_H) {
+    for (int m = 0; m < vc::MEL; ++m) s += (double)wo[(size_t)i * vc::MEL + m] * (double)w1[(size_t)m * vc::PRENET + o];
+    wc[(size_t)i * vc::PRENET + o] = (float)s;
+  } else {
+    for (int m = 0; m < vc::MEL; ++m) s += (double)bo[m] * (double)w1[(size_t)m * vc::PRENET + o];
+    bc[o] = (float)s;
   }
 }
 
@@ -495,9 +670,7 @@ constexpr size_t enc_scan_smem() {
   return ((size_t)(vc::ENC_D + NSLICE) * NCOL + RG * (vc::ENC_D + 4) + 8 * RG * NCOL + RG * NCOL + MAX_ROWS * UPC) * 4;
 }
 constexpr size_t dec_scan_smem() {
-  constexpr int K0 = vc::PRENET + vc::DEC_H, K1 = vc::PRENET + 2 * vc::DEC_H;
-  return ((size_t)(K0 + NSLICE) * NCOL + (size_t)(K1 + NSLICE) * NCOL + RG * (K1 + 4) + 8 * RG * NCOL + RG * NCOL +
-          2 * MAX_ROWS * UPC + vc::MEL * 2 + vc::PRENET * 2 + 2 * vc::DEC_H) * 4;
+  return ((size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + DEC_XR * NCOL + 2 * MAX_ROWS * UPC + 2 * vc::DEC_H * 8 + vc::PRENET * 2) * 4;
 }
 
 // derived-weight slots (ctx->ac_d)
@@ -507,9 +680,11 @@ enum {
   D_ENC_WHR,     // [2][64][256][16]
   D_DEC_W0R,     // [128][768][16]
   D_DEC_W1R,     // [128][1280][16]
-  D_DEC_WP1,     // [128][80][2]
+  D_DEC_WC,      // [32][1024][8]  (Wo . W1) columns
+  D_DEC_WCFULL,  // [1024][256] scratch
+  D_DEC_BC,      // [256]
   D_DEC_WP2,     // [128][256][2]
-  D_DEC_WO,      // [80][1024]
+  D_DEC_WO,      // [20][1024][4]
   D_COUNT
 };
 
@@ -518,7 +693,7 @@ enum {
 int vtts_acoustic_prepare(vtts_ctx* ctx) {
   const size_t sizes[D_COUNT] = {256, 256, 256, 512, 512, 512, 512,
                                  (size_t)2 * 64 * 256 * 16, (size_t)128 * 768 * 16, (size_t)128 * 1280 * 16,
-                                 (size_t)128 * 80 * 2, (size_t)128 * 256 * 2, (size_t)80 * 1024};
+                                 (size_t)128 * 1024 * 2, (size_t)1024 * 256, 256, (size_t)128 * 256 * 2, (size_t)80 * 1024};
   size_t total = 0;
   std::vector<size_t> offs(D_COUNT);
   for (int i = 0; i < D_COUNT; ++i) {
@@ -538,9 +713,10 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
   // decoder: rows after the 512 cond rows
   repack_cols_kernel<<<512, 256>>>(T[aci::DEC_L0_W], 2048, 512, 768, ctx->ac_d[D_DEC_W0R], 128, 16, UPC, 512);
   repack_cols_kernel<<<512, 256>>>(T[aci::DEC_L1_W], 2048, 512, 1280, ctx->ac_d[D_DEC_W1R], 128, 16, UPC, 512);
-  repack_cols_kernel<<<64, 256>>>(T[aci::PRE1_W], 256, 0, 80, ctx->ac_d[D_DEC_WP1], 128, 2, 2, 0);
+  precompose_kernel<<<2 * vc::DEC_H + 1, 256>>>(T[aci::PROJ_W], T[aci::PROJ_B], T[aci::PRE1_W], ctx->ac_d[D_DEC_WCFULL], ctx->ac_d[D_DEC_BC]);
+  repack_cols_kernel<<<256, 256>>>(ctx->ac_d[D_DEC_WCFULL], 256, 0, 1024, ctx->ac_d[D_DEC_WC], 32, 8, 8, 0);
   repack_cols_kernel<<<64, 256>>>(T[aci::PRE2_W], 256, 0, 256, ctx->ac_d[D_DEC_WP2], 128, 2, 2, 0);
-  repack_cols_kernel<<<64, 256>>>(T[aci::PROJ_W], 80, 0, 1024, ctx->ac_d[D_DEC_WO], 80, 1, 1, 0);
+  repack_cols_kernel<<<64, 256>>>(T[aci::PROJ_W], 80, 0, 1024, ctx->ac_d[D_DEC_WO], 20, 4, 4, 0);
   VTTS_CUDA(cudaGetLastError());
   VTTS_CUDA(cudaDeviceSynchronize());
   VTTS_CUDA(cudaFuncSetAttribute(enc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_scan_smem()));
@@ -647,11 +823,11 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   {
     DecScanArgs da;
     da.zc0 = zc0; da.zc1 = zc1;
-    da.w0r = D[D_DEC_W0R]; da.w1r = D[D_DEC_W1R]; da.wp1 = D[D_DEC_WP1]; da.wp2 = D[D_DEC_WP2];
+    da.w0r = D[D_DEC_W0R]; da.w1r = D[D_DEC_W1R]; da.wc = D[D_DEC_WC]; da.bc = D[D_DEC_BC]; da.wp2 = D[D_DEC_WP2];
     da.wo = D[D_DEC_WO]; da.bo = T[aci::PROJ_B];
     da.keep = keep; da.seed = seed; da.mode = mode;
     da.p1 = p1; da.p2 = p2; da.h0 = h0; da.h1 = h1; da.mel = melpre;
-    da.B = B; da.N = N; da.row_base = 0; da.B_total = B;
+    da.B = B; da.N = N;
     void* args[] = {&da};
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(SCAN_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
     ctx->launches++;

@@ -15,11 +15,11 @@
 //   B operand: weights pre-split and pre-packed at load time into the same canonical layout,
 //     streamed with cp.async.bulk (TMA bulk copy) through a 4-stage mbarrier ring.
 //
-// One persistent CTA per SM, 10 warps:
+// One persistent CTA per SM, 14 warps:
 //   warps 0-3  epilogue   tcgen05.ld TMEM -> regs, + bias (+ residual), fp32 NWC store
 //   warp  4    MMA issue  (one lane) + TMEM alloc/dealloc
 //   warp  5    weight producer (one lane, cp.async.bulk + expect_tx)
-//   warps 6-9  activation converters: fp32 global -> [mean3] -> leaky_relu -> hi/lo bf16 -> smem
+//   warps 6-13 activation converters: fp32 global -> [mean3] -> leaky_relu -> hi/lo bf16 -> smem
 // A "super tile" is MT = min(4, 512/N) M-tiles (128*MT rows) that share every weight stage, so a
 // weight block fetched from L2 feeds MT MMAs.
 #include <cuda_bf16.h>
@@ -30,7 +30,8 @@ namespace {
 
 constexpr int NA = 3;               // activation stages
 constexpr int NW = 4;               // weight stages
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 448;     // 4 epilogue + MMA + weight producer + 8 converter warps
+constexpr int NCONV = 256;        // converter threads
 constexpr long long SPIN_TIMEOUT = 4000000000LL;  // ~2 s of SM clocks: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 5 && lane == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], NCONV); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 128);
@@ -248,9 +249,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     __syncwarp();
   } else if (warp >= 6) {
     // ============================ activation converters ============================
-    const int ct = tid - 192;          // 0..127
+    const int ct = tid - 192;          // 0..255
     const int q = ct & 3;              // 4-channel group inside the 16-channel chunk
-    const int r0 = ct >> 2;            // 0..31
+    const int r0 = ct >> 2;            // 0..63
     const int pre_mode = L.pre_mode;
     const float slope = L.pre_slope;
     const int ld = L.in_ld;
@@ -267,11 +268,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
         mbar_wait(&a_empty[sa], pa ^ 1, L.err, 5);
         uint8_t* st = a_st + sa * Cfg::A_STAGE + ((q >> 1) * RA) * 16 + (q & 1) * 8;
         const int coff = c * 16 + q * 4;
-        for (int rr0 = r0; rr0 < rows; rr0 += 128) {
-          float4 v[4];
+        constexpr int U = 8;           // loads in flight per thread (memory-level parallelism)
+        for (int rr0 = r0; rr0 < rows; rr0 += 64 * U) {
+          float4 v[U];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rr = rr0 + u * 32;
+          for (int u = 0; u < U; ++u) {
+            const int rr = rr0 + u * 64;
             const int t = row_base + rr;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rr < rows && t >= 0 && t < valid) {
@@ -288,8 +290,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rr = rr0 + u * 32;
+          for (int u = 0; u < U; ++u) {
+            const int rr = rr0 + u * 64;
             if (rr < rows) {
               float4 x = v[u];
               if (pre_mode >= 1) {
@@ -408,7 +410,7 @@ int vtts_tc_pack_weights(vtts_ctx* ctx, const float* w, void* dst, int k, int Ci
 }
 
 int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
-  if (L.nprob < 1 || L.nprob > 3) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: nprob %d", L.nprob);
+  if (L.nprob < 1 || L.nprob > 8) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: nprob %d", L.nprob);
   if (L.Cin % 16 != 0) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: Cin %d", L.Cin);
   for (int i = 0; i < L.nprob; ++i)
     if ((L.p[i].k - 1) * L.p[i].dil > 50 || L.p[i].k < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: halo too large");

@@ -81,7 +81,7 @@ struct TcProb {
 };
 
 struct TcLaunch {
-  TcProb p[3];
+  TcProb p[8];
   int nprob;
   int Cin, N;            // N = output channels of this launch (32/64/128/256)
   int in_ld, out_ld;     // row strides in floats
@@ -96,10 +96,12 @@ struct TcLaunch {
 
 struct vtts_ctx {
   int device = 0;
-  int precision = 0;            // 0 = strict fp32 (FMA pipe), 1 = bf16x3 on tcgen05 tensor cores
+  int precision = 1;            // 0 = strict fp32 (FMA pipe), 1 = bf16x3 on tcgen05 tensor cores (default)
   int* d_err = nullptr;
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
+  std::vector<void*> hg_wpk_ups;   // [stage][phase] packed transposed-conv phase weights
+  void* hg_wpk_pre[2] = {nullptr, nullptr};  // conv_pre, two N=256 output tiles
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   size_t hbm_bytes = 0;
