@@ -112,6 +112,13 @@ int vtts_debug_conv1d(vtts_ctx* ctx, int precision, const float* x_dev, const fl
                       const float* resid_dev, const int32_t* len_dev, int B, int T, int Cin, int Cout, int k, int dil,
                       float pre_slope, float* out_dev);
 
+/* profiling aid: per-CTA stall counters (SM clocks) of the LAST tensor-core conv launch.
+ * Row = CTA, columns: 0 MMA-role total, 1 MMA wait accumulator-free, 2 MMA wait activations, 3 MMA wait
+ * weights, 4 weight-producer wait slot, 5 converter wait slot, 6 converter fill, 7 epilogue wait
+ * accumulator, 8 epilogue drain.  enable!=0 turns collection on for later launches; the call
+ * synchronises, copies (if host_out != NULL) and clears the counters. */
+int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16);
+
 /* ---- host-buffer entry points (what a ctypes / cgo / JNI binding calls) ------------------ */
 int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav);
 int vtts_predict_mel_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths,

@@ -14,11 +14,14 @@ pytestmark = pytest.mark.gpu
 MEL_LINF = 1e-3
 
 
-@pytest.fixture(scope="module")
-def eng(acoustic_ckpt):
+@pytest.fixture(scope="module", params=["fp32", "bf16x3"])
+def eng(acoustic_ckpt, request):
+    """Both arithmetic paths of the dense contractions (convs + hoisted LSTM input GEMMs) must meet
+    the same tolerance; the recurrent part is fp32 in both."""
     from viettts_b200.engine import Engine
     e = Engine(0)
     e.load_acoustic(acoustic_ckpt)
+    e.set_precision(request.param)
     yield e
     e.close()
 

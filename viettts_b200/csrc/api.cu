@@ -221,6 +221,12 @@ int vtts_create(int device, vtts_ctx** out) {
     delete ctx;
     return VTTS_ERR_CUDA;
   }
+  if (cudaMalloc(&ctx->d_tc_dbg, 256 * 16 * sizeof(long long)) != cudaSuccess) {
+    g_vtts_create_error = "vtts_create: cannot allocate the profiling counters";
+    delete ctx;
+    return VTTS_ERR_CUDA;
+  }
+  cudaMemset(ctx->d_tc_dbg, 0, 256 * 16 * sizeof(long long));
   *out = ctx;
   return VTTS_OK;
 }
@@ -231,7 +237,7 @@ int vtts_destroy(vtts_ctx* ctx) {
   cudaDeviceSynchronize();
   cudaFree(ctx->hg_blob); cudaFree(ctx->hg_upsw); cudaFree(ctx->ac_blob); cudaFree(ctx->ac_derived);
   cudaFree(ctx->mel_fb); cudaFree(ctx->mel_lo); cudaFree(ctx->mel_hi); cudaFree(ctx->fft_tw); cudaFree(ctx->hann);
-  cudaFree(ctx->ws); cudaFree(ctx->dstage); cudaFree(ctx->d_err); cudaFree(ctx->hg_wpk);
+  cudaFree(ctx->ws); cudaFree(ctx->dstage); cudaFree(ctx->d_err); cudaFree(ctx->hg_wpk); cudaFree(ctx->ac_wpk); cudaFree(ctx->d_tc_dbg);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
   for (int i = 0; i < 3; ++i) {
     cudaEventDestroy(ctx->ev0[i]);
@@ -262,6 +268,16 @@ int vtts_set_precision(vtts_ctx* ctx, int mode) {
 
 int vtts_get_precision(vtts_ctx* ctx) { return ctx ? ctx->precision : VTTS_ERR_BAD_ARG; }
 
+int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  VTTS_CUDA(cudaDeviceSynchronize());
+  if (host_out_256x16) VTTS_CUDA(cudaMemcpy(host_out_256x16, ctx->d_tc_dbg, 256 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  VTTS_CUDA(cudaMemset(ctx->d_tc_dbg, 0, 256 * 16 * sizeof(long long)));
+  ctx->tc_dbg_on = enable != 0;
+  return VTTS_OK;
+}
+
 int vtts_debug_conv1d(vtts_ctx* ctx, int precision, const float* x_dev, const float* w_dev, const float* bias_dev,
                       const float* resid_dev, const int32_t* len_dev, int B, int T, int Cin, int Cout, int k, int dil,
                       float pre_slope, float* out_dev) {
@@ -284,7 +300,7 @@ int vtts_debug_conv1d(vtts_ctx* ctx, int precision, const float* x_dev, const fl
     memset(&TL, 0, sizeof(TL));
     TL.nprob = 1; TL.Cin = Cin; TL.N = Cout; TL.in_ld = Cin; TL.out_ld = Cout; TL.B = B; TL.T_rows = T; TL.rows_out = T;
     TL.len = len_dev; TL.len_mul = 1; TL.pre_mode = pre_slope == 1.0f ? 0 : 1; TL.pre_slope = pre_slope;
-    TL.p[0] = TcProb{x_dev, nullptr, nullptr, wpk, bias_dev, resid_dev, out_dev, k, dil, -((k - 1) * dil) / 2, 1, 0};
+    TL.p[0] = TcProb{x_dev, nullptr, nullptr, wpk, bias_dev, resid_dev, nullptr, nullptr, nullptr, out_dev, k, dil, -((k - 1) * dil) / 2, 1, 0};
     rc = vtts_launch_tc_conv(ctx, TL, nullptr);
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(wpk);

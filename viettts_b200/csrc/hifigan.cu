@@ -216,7 +216,7 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
     TL.nprob = 2; TL.Cin = vc::MEL; TL.N = 256; TL.in_ld = vc::MEL; TL.out_ld = vc::HG_C0;
     TL.B = B; TL.T_rows = T; TL.rows_out = T; TL.len = n_frames; TL.len_mul = 1; TL.pre_mode = 0; TL.pre_slope = 1.f;
     for (int t = 0; t < 2; ++t)
-      TL.p[t] = TcProb{mel, nullptr, nullptr, ctx->hg_wpk_pre[t], W[hgi::PRE_B] + 256 * t, nullptr, hb.P0 + 256 * t, 7, 1, -3, 1, 0};
+      TL.p[t] = TcProb{mel, nullptr, nullptr, ctx->hg_wpk_pre[t], W[hgi::PRE_B] + 256 * t, nullptr, nullptr, nullptr, nullptr, hb.P0 + 256 * t, 7, 1, -3, 1, 0};
     rc = vtts_launch_tc_conv(ctx, TL, st);
   } else {
     rc = vtts_launch_conv(ctx, L, st);
@@ -257,7 +257,7 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
       TL.pre_mode = L.pre_mode; TL.pre_slope = 0.1f;
       for (int r = 0; r < u; ++r) {
         const ConvProb& cp = L.p[r];
-        TL.p[r] = TcProb{cp.x0, cp.x1, cp.x2, ctx->hg_wpk_ups[i * 8 + r], cp.bias, nullptr, cp.out, 2, 1, cp.in_off, u, r};
+        TL.p[r] = TcProb{cp.x0, cp.x1, cp.x2, ctx->hg_wpk_ups[i * 8 + r], cp.bias, nullptr, nullptr, nullptr, nullptr, cp.out, 2, 1, cp.in_off, u, r};
       }
       rc = vtts_launch_tc_conv(ctx, TL, st);
     } else {

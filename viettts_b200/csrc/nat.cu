@@ -89,6 +89,18 @@ __global__ void repack_cols_kernel(const float* __restrict__ src, int ld, int ro
   }
 }
 
+// projection weights [1024][80] -> [4 CTAs][3 passes][1024 + 64 pad rows][8], already in the padded layout
+// pre_gemm8 reads (physical row = k + k/16); columns beyond the CTA's 20 are zero.
+__global__ void repack_proj_kernel(const float* __restrict__ src, float* __restrict__ dst) {
+  const int total = 4 * 3 * 1024 * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c8 = idx % 8, k = (idx / 8) % 1024, ps = (idx / (8 * 1024)) % 3, q = idx / (8 * 1024 * 3);
+    const int lc = ps * 8 + c8;
+    const float v = lc < 20 ? src[(size_t)k * vc::MEL + q * 20 + lc] : 0.f;
+    dst[(((size_t)q * 3 + ps) * (1024 + 64) + k + k / 16) * 8 + c8] = v;
+  }
+}
+
 __global__ void fill_kernel(int32_t* p, int v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -340,26 +352,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) enc_scan_kernel(const EncScan
 }
 
 // ---- autoregressive decoder scan (model.py:129-142) ------------------------------------------------
-// Per frame t (B rows at once), four grid-wide phases:
-//   EA  p1(t) = drop(relu(mel_{t-1} . W1))  computed as relu([h0,h1]_{t-1} . (Wo.W1) + bo.W1)  (2 cols / CTA)
-//       and mel_{t-1} = [h0,h1]_{t-1} . Wo + bo  (the output frame, CTAs 0..79)
-//   B   p2(t) = drop(relu(p1 . W2))                                                        (2 cols / CTA)
-//   C   LSTM0: z = zc0[t] + [p2, h0_{t-1}] . W0r ; gates -> h0_t                             (4 units / CTA)
-//   D   LSTM1: z = zc1[t] + [p2, h0_t, h1_{t-1}] . W1r ; gates -> h1_t
-// The CTA's slices of the recurrent matrices (768x16 and 1280x16 fp32 = 128 KB) live in REGISTERS:
-// thread (ks, cg) owns K-slice ks (12 / 20 rows) x 4 gate columns of both layers, so shared memory is
-// free to hold the input vectors of all 32 batch rows and each phase costs a single L2 round trip.
+// One cooperative grid of 148 CTAs, up to 32 batch rows per launch.
+//   CTAs 0..127   LSTM role: CTA c owns 4 hidden units (16 gate columns) of both layers; its slices of the
+//                 recurrent matrices (768x16 + 1280x16 fp32) live in REGISTERS.  A persistent shared-memory
+//                 buffer holds [p2 | h0 | h1] of all rows; the parts that are already final (h0_{t-1},
+//                 h1_{t-1}) are prefetched while the prenet CTAs work, so only p2 (phase C) and h0_t (phase D)
+//                 are fetched on the critical path.
+//   CTAs 128..143 prenet role: 16 columns each of p1 = drop(relu([h0,h1]_{t-1}.(Wo.W1) + bo.W1))  (phase EA)
+//                 and of p2 = drop(relu(p1.W2))                                                   (phase B)
+//   CTAs 144..147 projection role: 20 columns each of mel_{t-1} = [h0,h1]_{t-1}.Wo + bo, computed off the
+//                 critical path (during phase C of the next frame).
+// Four grid barriers per frame: EA | B | C (LSTM0) | D (LSTM1).
 struct DecScanArgs {
   const float* zc0;      // [B][N][2048] cond.W0[0:512] + b0
   const float* zc1;      // [B][N][2048] cond.W1[0:512] + b1
   const float* w0r;      // [128][768][16]   rows 512..1279 of lstm0   ([p2, h0])
   const float* w1r;      // [128][1280][16]  rows 512..1791 of lstm1   ([p2, h0, h1])
-  const float* wc;       // [32][1024][8]    (Wo . W1) columns, 8 per EA CTA
+  const float* wc;       // [16][1024][16]   (Wo . W1) columns, 16 per prenet CTA
   const float* bc;       // [256]            bo . W1
-  const float* wp2;      // [128][256][2]    prenet fc2 columns
-  const float* wo;       // [20][1024][4]    projection columns, 4 per EA CTA
+  const float* wp2;      // [16][256][16]    prenet fc2 columns
+  const float* wo;       // [4][3][1088][8]  projection columns in pre_gemm8 layout, 20 per projection CTA
   const float* bo;       // [80]
-  const uint8_t* keep;   // [B][N][2][256] or null
+  const uint8_t* keep;   // [B][N][2][256] or null (indexed with row_base)
   uint64_t seed;
   int mode;
   float* p1;             // [B][256]
@@ -367,41 +381,42 @@ struct DecScanArgs {
   float* h0;             // [2][B][512]
   float* h1;             // [2][B][512]
   float* mel;            // [B][N][80]  (pre-postnet output)
-  int B, N;
+  int B, N;              // rows of this launch (<= 32), frames
+  int row_base;          // first row of this launch inside the full batch (dropout stream indexing)
+  int N_total_rows;      // unused
+  long long* dbg;        // optional per-CTA phase timers [grid][16]
 };
 
-constexpr int DEC_XR = 32;                 // batch rows staged at once
-constexpr int DEC_KPAD = vc::PRENET + 2 * vc::DEC_H + 4;   // 1284
+constexpr int DEC_XR = 32;                 // batch rows per launch
+constexpr int DEC_KPAD = vc::PRENET + 2 * vc::DEC_H + 4;   // 1284: [p2 | h0 | h1] + pad
+constexpr int DEC_CTAS = 148;
+constexpr int DEC_LSTM = 128, DEC_PRE = 16, DEC_PROJ = 4;
+constexpr int PRE_KP = 2 * vc::DEC_H + 4;  // 1028: row pitch of the prenet CTAs' [h0 | h1] buffer
 
-// stage rows [row0,row0+nr) of up to 3 concatenated segments into xs[r][DEC_KPAD]
-__device__ __forceinline__ void dec_stage(float* xs, const Seg* segs, int nseg, int row0, int nr) {
-  int koff = 0;
-  for (int s = 0; s < nseg; ++s) {
-    const int n4 = segs[s].n >> 2;
-    const int total = nr * n4;
-    const float* p = segs[s].p;
-    const int stride = segs[s].stride;
-    for (int e0 = threadIdx.x; e0 < total; e0 += SCAN_THREADS * 8) {
-      float4 v[8];
+// copy rows [0,nr) x [n floats] of a global matrix (row stride `stride`) into smem (row pitch `pitch`, column
+// offset koff); p == nullptr writes zeros.  8 x 16 B loads in flight per thread.
+__device__ __forceinline__ void dec_fetch(float* xs, int pitch, int koff, const float* p, int n, int stride, int nr) {
+  const int n4 = n >> 2;
+  const int total = nr * n4;
+  for (int e0 = threadIdx.x; e0 < total; e0 += SCAN_THREADS * 8) {
+    float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + u * SCAN_THREADS;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < total && p) {
-          const int r = e / n4, i4 = (e - r * n4) * 4;
-          v[u] = __ldcg(reinterpret_cast<const float4*>(p + (size_t)(row0 + r) * stride + i4));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + u * SCAN_THREADS;
-        if (e < total) {
-          const int r = e / n4, i4 = (e - r * n4) * 4;
-          *reinterpret_cast<float4*>(xs + (size_t)r * DEC_KPAD + koff + i4) = v[u];
-        }
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * SCAN_THREADS;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < total && p) {
+        const int r = e / n4, i4 = (e - r * n4) * 4;
+        v[u] = __ldcg(reinterpret_cast<const float4*>(p + (size_t)r * stride + i4));
       }
     }
-    koff += segs[s].n;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * SCAN_THREADS;
+      if (e < total) {
+        const int r = e / n4, i4 = (e - r * n4) * 4;
+        *reinterpret_cast<float4*>(xs + (size_t)r * pitch + koff + i4) = v[u];
+      }
+    }
   }
 }
 
@@ -437,10 +452,9 @@ __device__ __forceinline__ float4 warp_reduce_rows(float (&acc)[RG][4], int lane
   return make_float4(a1[0], a1[1], a1[2], a1[3]);
 }
 
-// one LSTM layer for up to DEC_XR staged rows: z partials -> part[warp][row][16] -> zs[row][16]
+// one LSTM layer for the staged rows: z partials -> part[warp][row][16] -> zs[row][16]
 template <int SL>
-__device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, int koff_unused, const float (&w)[SL][4], int ngroups,
-                                           float* part, float* zs) {
+__device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const float (&w)[SL][4], int ngroups, float* part, float* zs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ks = tid >> 2;
   for (int g = 0; g < ngroups; ++g) {
@@ -463,7 +477,6 @@ __device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, int kof
       }
     }
     const float4 s = warp_reduce_rows(acc, lane);
-    // row (lane>>2) of group g, columns (lane&3)*4..+3
     *reinterpret_cast<float4*>(part + ((size_t)warp * DEC_XR + g * RG + (lane >> 2)) * NCOL + (lane & 3) * 4) = s;
   }
   __syncthreads();
@@ -476,179 +489,270 @@ __device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, int kof
   __syncthreads();
 }
 
+// ---- prenet / projection CTAs: out[32 rows][8 cols] = xs[32][K] . wsm[K][8] ------------------------------
+// thread (rg = tid&3, ks = tid>>2): rows rg+4i (i<8), K slice ks of SL = K/64; weights in smem with one pad
+// row per slice (physical row = k + k/SL).  Result: outv[row*8 + col] for 32 x 8 outputs.
+template <int SL>
+__device__ __forceinline__ void pre_gemm8(const float* __restrict__ xs, int pitch, const float* __restrict__ wsm, float* part, float* outv) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = tid & 3, ks = tid >> 2;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+  const float* xk = xs + (size_t)rg * pitch + ks * SL;
+  const float* wk = wsm + (size_t)(ks * SL + ks) * 8;
+#pragma unroll
+  for (int kk = 0; kk < SL; kk += 4) {
+    float4 xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xk + (size_t)(4 * i) * pitch + kk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 wa = *reinterpret_cast<const float4*>(wk + (size_t)(kk + e) * 8);
+      const float4 wb = *reinterpret_cast<const float4*>(wk + (size_t)(kk + e) * 8 + 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = e == 0 ? xv[i].x : (e == 1 ? xv[i].y : (e == 2 ? xv[i].z : xv[i].w));
+        acc[i][0] = fmaf(x, wa.x, acc[i][0]); acc[i][1] = fmaf(x, wa.y, acc[i][1]);
+        acc[i][2] = fmaf(x, wa.z, acc[i][2]); acc[i][3] = fmaf(x, wa.w, acc[i][3]);
+        acc[i][4] = fmaf(x, wb.x, acc[i][4]); acc[i][5] = fmaf(x, wb.y, acc[i][5]);
+        acc[i][6] = fmaf(x, wb.z, acc[i][6]); acc[i][7] = fmaf(x, wb.w, acc[i][7]);
+      }
+    }
+  }
+  // butterfly over the 8 K slices of the warp (lane bits 2..4), halving the row set each time
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float a4[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float send = b4 ? acc[i][c] : acc[i + 4][c];
+      const float keep = b4 ? acc[i + 4][c] : acc[i][c];
+      a4[i][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  float a2[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float send = b3 ? a4[i][c] : a4[i + 2][c];
+      const float keep = b3 ? a4[i + 2][c] : a4[i][c];
+      a2[i][c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  float a1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float send = b2 ? a2[0][c] : a2[1][c];
+    const float keep = b2 ? a2[1][c] : a2[0][c];
+    a1[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  // this thread now holds row rg + 4*(lane>>2 & 7) ... = rg + 4*ksl, all 8 columns, summed over the warp's slices
+  const int row = rg + 4 * ((lane >> 2) & 7);
+  float* pw = part + ((size_t)warp * 32 + row) * 8;
+  *reinterpret_cast<float4*>(pw) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+  *reinterpret_cast<float4*>(pw + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+  __syncthreads();
+  {
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < SCAN_THREADS / 32; ++wv) sum += part[(size_t)wv * 256 + tid];
+    outv[tid] = sum;   // tid = row*8 + col
+  }
+  __syncthreads();
+}
+
+// copy a [K][ncols_src] slice (cols c0..c0+8) of a global per-CTA weight block into smem [K + K/SL][8]
+__device__ __forceinline__ void pre_load_w8(float* wsm, const float* g, int K, int SL, int ld, int c0) {
+  for (int e = threadIdx.x; e < K * 2; e += SCAN_THREADS) {
+    const int k = e >> 1, h = (e & 1) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + (size_t)k * ld + c0 + h));
+    *reinterpret_cast<float4*>(wsm + (size_t)(k + k / SL) * 8 + h) = v;
+  }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const DecScanArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float sm[];
   constexpr int H = vc::DEC_H, K0 = vc::PRENET + H, K1 = vc::PRENET + 2 * H;
   constexpr int SL0 = K0 / NSLICE, SL1 = K1 / NSLICE;   // 12, 20
-  float* xs = sm;                                   // [DEC_XR][DEC_KPAD]
-  float* part = xs + DEC_XR * DEC_KPAD;             // [8][DEC_XR][16]
-  float* zs = part + 8 * DEC_XR * NCOL;             // [DEC_XR][16]
-  float* cst = zs + DEC_XR * NCOL;                  // [2][MAX_ROWS][UPC]
-  float* wea = cst + 2 * MAX_ROWS * UPC;            // [1024][8]: CTAs 0..31 (Wo.W1) cols 8c..8c+7; CTAs 32..51 Wo cols 4(c-32)..+3 ([1024][4])
-  float* wp2 = wea + 2 * H * 8;                     // [256][2]
-  const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ks = tid >> 2, cgp = tid & 3;
+  const int c = blockIdx.x, tid = threadIdx.x;
   const int B = a.B, N = a.N;
+  long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tq = clock64();
+#define DEC_MARK(i) { const long long tn = clock64(); tm[i] += tn - tq; tq = tn; }
 
-  // ---- register-resident recurrent weight slices ----
-  float w0[SL0][4], w1[SL1][4];
-  {
-    const float* g0 = a.w0r + ((size_t)c * K0 + ks * SL0) * NCOL + cgp * 4;
+  if (c < DEC_LSTM) {
+    // =============================== LSTM role ===============================
+    float* xs = sm;                                   // [DEC_XR][DEC_KPAD] = [p2 | h0 | h1]
+    float* part = xs + DEC_XR * DEC_KPAD;             // [8][DEC_XR][16]
+    float* zs = part + 8 * DEC_XR * NCOL;             // [DEC_XR][16]
+    float* cst = zs + DEC_XR * NCOL;                  // [2][DEC_XR][UPC]
+    const int ks = tid >> 2, cgp = tid & 3;
+    float w0[SL0][4], w1[SL1][4];
+    {
+      const float* g0 = a.w0r + ((size_t)c * K0 + ks * SL0) * NCOL + cgp * 4;
 #pragma unroll
-    for (int i = 0; i < SL0; ++i) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(g0 + (size_t)i * NCOL));
-      w0[i][0] = v.x; w0[i][1] = v.y; w0[i][2] = v.z; w0[i][3] = v.w;
-    }
-    const float* g1 = a.w1r + ((size_t)c * K1 + ks * SL1) * NCOL + cgp * 4;
+      for (int i = 0; i < SL0; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g0 + (size_t)i * NCOL));
+        w0[i][0] = v.x; w0[i][1] = v.y; w0[i][2] = v.z; w0[i][3] = v.w;
+      }
+      const float* g1 = a.w1r + ((size_t)c * K1 + ks * SL1) * NCOL + cgp * 4;
 #pragma unroll
-    for (int i = 0; i < SL1; ++i) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(g1 + (size_t)i * NCOL));
-      w1[i][0] = v.x; w1[i][1] = v.y; w1[i][2] = v.z; w1[i][3] = v.w;
+      for (int i = 0; i < SL1; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g1 + (size_t)i * NCOL));
+        w1[i][0] = v.x; w1[i][1] = v.y; w1[i][2] = v.z; w1[i][3] = v.w;
+      }
     }
-  }
-  for (int e = tid; e < 2 * MAX_ROWS * UPC; e += SCAN_THREADS) cst[e] = 0.f;
-  constexpr int EA_P1 = 32, EA_MEL = 20;            // CTAs computing p1 (8 cols each) / mel (4 cols each)
-  if (c < EA_P1)
-    for (int e = tid; e < 2 * H * 8; e += SCAN_THREADS) wea[e] = a.wc[(size_t)c * 2 * H * 8 + e];
-  else if (c < EA_P1 + EA_MEL)
-    for (int e = tid; e < 2 * H * 4; e += SCAN_THREADS) wea[e] = a.wo[(size_t)(c - EA_P1) * 2 * H * 4 + e];
-  for (int e = tid; e < vc::PRENET * 2; e += SCAN_THREADS) wp2[e] = a.wp2[(size_t)c * vc::PRENET * 2 + e];
-  __syncthreads();
-
-  for (int t = 0; t <= N; ++t) {
-    const int cur = t & 1, prv = cur ^ 1;
-    // ---- phase EA: mel_{t-1} (CTAs 32..51, 4 cols each) and p1(t) (CTAs 0..31, 8 cols each) from [h0,h1]_{t-1} ----
-    if (t > 0 && c < EA_P1 + EA_MEL) {
-      const bool is_p1 = c < EA_P1;
-      for (int row0 = 0; row0 < B; row0 += DEC_XR) {
-        const int nr = min(DEC_XR, B - row0);
-        Seg segs[2];
-        segs[0] = Seg{a.h0 + (size_t)prv * B * H, H, H};
-        segs[1] = Seg{a.h1 + (size_t)prv * B * H, H, H};
-        dec_stage(xs, segs, 2, row0, nr);
+    for (int e = tid; e < 2 * DEC_XR * UPC; e += SCAN_THREADS) cst[e] = 0.f;
+    for (int e = tid; e < DEC_XR * DEC_KPAD; e += SCAN_THREADS) xs[e] = 0.f;   // rows >= B and the t=0 state are zero
+    __syncthreads();
+    const int ngroups = (B + RG - 1) / RG;
+    for (int t = 0; t < N; ++t) {
+      const int cur = t & 1, prv = cur ^ 1;
+      // ---- EA window: prefetch the state vectors that are already final: h0_{t-1}, h1_{t-1} ----
+      if (t > 0) {
+        dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)prv * B * H, H, H, B);
+        dec_fetch(xs, DEC_KPAD, vc::PRENET + H, a.h1 + (size_t)prv * B * H, H, H, B);
+      }
+      DEC_MARK(0)
+      grid.sync();
+      DEC_MARK(1)
+      // ---- B window: nothing to do ----
+      DEC_MARK(2)
+      grid.sync();
+      DEC_MARK(3)
+      // ---- phase C: LSTM0 on [cond_t (hoisted), p2, h0_{t-1}] ----
+      dec_fetch(xs, DEC_KPAD, 0, a.p2, vc::PRENET, vc::PRENET, B);
+      __syncthreads();
+      dec_matmul<SL0>(xs, w0, ngroups, part, zs);
+      if (tid < B * UPC) {
+        const int r = tid / UPC, uu = tid % UPC;
+        const float* zc = a.zc0 + ((size_t)r * N + t) * (4 * H) + c * UPC + uu;
+        float cc = cst[r * UPC + uu];
+        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
+        cst[r * UPC + uu] = cc;
+        a.h0[((size_t)cur * B + r) * H + c * UPC + uu] = h;
+      }
+      DEC_MARK(4)
+      grid.sync();
+      DEC_MARK(5)
+      // ---- phase D: LSTM1 on [cond_t (hoisted), p2, h0_t, h1_{t-1}] ----
+      dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)cur * B * H, H, H, B);
+      __syncthreads();
+      dec_matmul<SL1>(xs, w1, ngroups, part, zs);
+      if (tid < B * UPC) {
+        const int r = tid / UPC, uu = tid % UPC;
+        const float* zc = a.zc1 + ((size_t)r * N + t) * (4 * H) + c * UPC + uu;
+        float cc = cst[(DEC_XR + r) * UPC + uu];
+        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
+        cst[(DEC_XR + r) * UPC + uu] = cc;
+        a.h1[((size_t)cur * B + r) * H + c * UPC + uu] = h;
+      }
+      __syncthreads();
+      DEC_MARK(6)
+      grid.sync();
+      DEC_MARK(7)
+    }
+  } else if (c < DEC_LSTM + DEC_PRE) {
+    // =============================== prenet role ===============================
+    const int q = c - DEC_LSTM;                        // columns 16q .. 16q+15 of p1 and p2
+    float* xs = sm;                                    // [32][PRE_KP]  (phase EA: [h0|h1]; phase B: p1 in the first 260 floats)
+    float* wcs = xs + 32 * PRE_KP;                     // [2][1024+64][8]
+    float* w2s = wcs + 2 * (2 * H + NSLICE) * 8;       // [2][256+64][8]
+    float* part = w2s + 2 * (vc::PRENET + NSLICE) * 8; // [8][32][8]
+    float* outv = part + 8 * 256;                      // [256]
+    for (int hf = 0; hf < 2; ++hf) {
+      pre_load_w8(wcs + (size_t)hf * (2 * H + NSLICE) * 8, a.wc + (size_t)q * 2 * H * 16, 2 * H, 16, 16, hf * 8);
+      pre_load_w8(w2s + (size_t)hf * (vc::PRENET + NSLICE) * 8, a.wp2 + (size_t)q * vc::PRENET * 16, vc::PRENET, 4, 16, hf * 8);
+    }
+    for (int e = tid; e < 32 * PRE_KP; e += SCAN_THREADS) xs[e] = 0.f;
+    __syncthreads();
+    const int orow = tid >> 3, ocol = tid & 7;         // output handled by this thread after a pre_gemm8 pass
+    for (int t = 0; t < N; ++t) {
+      const int prv = (t & 1) ^ 1;
+      // ---- phase EA: p1(t) ----
+      if (t > 0) {
+        dec_fetch(xs, PRE_KP, 0, a.h0 + (size_t)prv * B * H, H, H, B);
+        dec_fetch(xs, PRE_KP, H, a.h1 + (size_t)prv * B * H, H, H, B);
         __syncthreads();
-        for (int r = warp; r < nr; r += SCAN_THREADS / 32) {
-          const float* x = xs + (size_t)r * DEC_KPAD;
-          const int b = row0 + r;
-          if (is_p1) {
-            float s[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s[q] = 0.f;
-#pragma unroll 4
-            for (int i = lane; i < 2 * H; i += 32) {
-              const float xv = x[i];
-              const float4 wa = *reinterpret_cast<const float4*>(wea + i * 8);
-              const float4 wb = *reinterpret_cast<const float4*>(wea + i * 8 + 4);
-              s[0] = fmaf(xv, wa.x, s[0]); s[1] = fmaf(xv, wa.y, s[1]); s[2] = fmaf(xv, wa.z, s[2]); s[3] = fmaf(xv, wa.w, s[3]);
-              s[4] = fmaf(xv, wb.x, s[4]); s[5] = fmaf(xv, wb.y, s[5]); s[6] = fmaf(xv, wb.z, s[6]); s[7] = fmaf(xv, wb.w, s[7]);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
-            }
-            if (lane < 8 && t < N) {
-              float v = s[0];
-#pragma unroll
-              for (int q = 1; q < 8; ++q) v = lane == q ? s[q] : v;
-              const int u = c * 8 + lane;
-              v = fmaxf(v + __ldg(a.bc + u), 0.f);
-              a.p1[(size_t)b * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, b, t, N, 0, u);
-            }
-          } else {
-            float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-            for (int i = lane; i < 2 * H; i += 32) {
-              const float xv = x[i];
-              const float4 wa = *reinterpret_cast<const float4*>(wea + i * 4);
-              s[0] = fmaf(xv, wa.x, s[0]); s[1] = fmaf(xv, wa.y, s[1]); s[2] = fmaf(xv, wa.z, s[2]); s[3] = fmaf(xv, wa.w, s[3]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
-            }
-            if (lane < 4) {
-              float v = s[0];
-#pragma unroll
-              for (int q = 1; q < 4; ++q) v = lane == q ? s[q] : v;
-              const int m = (c - EA_P1) * 4 + lane;
-              a.mel[((size_t)b * N + (t - 1)) * vc::MEL + m] = v + __ldg(a.bo + m);
-            }
+        for (int hf = 0; hf < 2; ++hf) {
+          pre_gemm8<16>(xs, PRE_KP, wcs + (size_t)hf * (2 * H + NSLICE) * 8, part, outv);
+          if (orow < B) {
+            const int u = q * 16 + hf * 8 + ocol;
+            const float v = fmaxf(outv[tid] + __ldg(a.bc + u), 0.f);
+            a.p1[(size_t)orow * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + orow, t, N, 0, u);
           }
         }
-        __syncthreads();
+      } else if (tid < 32 * 16) {
+        for (int e = tid; e < B * 16; e += SCAN_THREADS) a.p1[(size_t)(e >> 4) * vc::PRENET + q * 16 + (e & 15)] = 0.f;  // prenet(0) = 0
       }
-    } else if (t == 0) {
-      for (int e = tid; e < B * 2; e += SCAN_THREADS) a.p1[(size_t)(e >> 1) * vc::PRENET + c * 2 + (e & 1)] = 0.f;  // prenet(0) = 0
-    }
-    if (t == N) break;
-    grid.sync();
-    // ---- phase B: p2 = dropout(relu(p1 . W2)) ----
-    for (int b = warp; b < B; b += SCAN_THREADS / 32) {
-      float s0 = 0.f, s1 = 0.f;
-      const float* p = a.p1 + (size_t)b * vc::PRENET;
-#pragma unroll
-      for (int i = lane; i < vc::PRENET; i += 32) {
-        const float x = __ldcg(p + i);
-        s0 = fmaf(x, wp2[i * 2 + 0], s0);
-        s1 = fmaf(x, wp2[i * 2 + 1], s1);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      }
-      if (lane < 2) {
-        const float v = fmaxf(lane == 0 ? s0 : s1, 0.f);
-        const int u = c * 2 + lane;
-        a.p2[(size_t)b * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, b, t, N, 1, u);
-      }
-    }
-    grid.sync();
-    // ---- phase C: LSTM0 on [cond_t (hoisted), p2, h0_prev] ----
-    for (int row0 = 0; row0 < B; row0 += DEC_XR) {
-      const int nr = min(DEC_XR, B - row0);
-      Seg segs[2];
-      segs[0] = Seg{a.p2, vc::PRENET, vc::PRENET};
-      segs[1] = Seg{t == 0 ? nullptr : a.h0 + (size_t)prv * B * H, H, H};
-      dec_stage(xs, segs, 2, row0, nr);
+      DEC_MARK(0)
+      grid.sync();
+      DEC_MARK(1)
+      // ---- phase B: p2(t) = drop(relu(p1 . W2)) ----
+      dec_fetch(xs, PRE_KP, 0, a.p1, vc::PRENET, vc::PRENET, B);
       __syncthreads();
-      dec_matmul<SL0>(xs, 0, w0, (nr + RG - 1) / RG, part, zs);
-      if (tid < nr * UPC) {
-        const int r = tid / UPC, uu = tid % UPC, b = row0 + r;
-        const float* zc = a.zc0 + ((size_t)b * N + t) * (4 * H) + c * UPC + uu;
-        float cc = cst[b * UPC + uu];
-        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
-        cst[b * UPC + uu] = cc;
-        a.h0[((size_t)cur * B + b) * H + c * UPC + uu] = h;
+      for (int hf = 0; hf < 2; ++hf) {
+        pre_gemm8<4>(xs, PRE_KP, w2s + (size_t)hf * (vc::PRENET + NSLICE) * 8, part, outv);
+        if (orow < B) {
+          const int u = q * 16 + hf * 8 + ocol;
+          const float v = fmaxf(outv[tid], 0.f);
+          a.p2[(size_t)orow * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + orow, t, N, 1, u);
+        }
       }
-      __syncthreads();
+      DEC_MARK(2)
+      grid.sync();
+      DEC_MARK(3)
+      grid.sync();
+      DEC_MARK(5)
+      grid.sync();
+      DEC_MARK(7)
     }
-    grid.sync();
-    // ---- phase D: LSTM1 on [cond_t (hoisted), p2, h0_t, h1_prev] ----
-    for (int row0 = 0; row0 < B; row0 += DEC_XR) {
-      const int nr = min(DEC_XR, B - row0);
-      Seg segs[3];
-      segs[0] = Seg{a.p2, vc::PRENET, vc::PRENET};
-      segs[1] = Seg{a.h0 + (size_t)cur * B * H, H, H};
-      segs[2] = Seg{t == 0 ? nullptr : a.h1 + (size_t)prv * B * H, H, H};
-      dec_stage(xs, segs, 3, row0, nr);
+  } else {
+    // =============================== projection role ===============================
+    const int q = c - DEC_LSTM - DEC_PRE;              // mel columns 20q .. 20q+19 (3 passes of 8, last padded)
+    constexpr int WBLK = (2 * H + NSLICE) * 8;         // one pass of weights in pre_gemm8 layout
+    float* xs = sm;                                    // [32][PRE_KP]
+    float* wos = xs + 32 * PRE_KP;                     // passes 0 and 1 in smem; pass 2 (4 real columns) is read from L2/L1
+    float* part = wos + 2 * WBLK;                      // [8][32][8]
+    float* outv = part + 8 * 256;
+    const float* wg = a.wo + (size_t)q * 3 * WBLK;
+    for (int e = tid; e < 2 * WBLK / 4; e += SCAN_THREADS)
+      reinterpret_cast<float4*>(wos)[e] = __ldg(reinterpret_cast<const float4*>(wg) + e);
+    for (int e = tid; e < 32 * PRE_KP; e += SCAN_THREADS) xs[e] = 0.f;
+    __syncthreads();
+    const int orow = tid >> 3, ocol = tid & 7;
+    auto stage = [&](int buf) {
+      dec_fetch(xs, PRE_KP, 0, a.h0 + (size_t)buf * B * H, H, H, B);
+      dec_fetch(xs, PRE_KP, H, a.h1 + (size_t)buf * B * H, H, H, B);
       __syncthreads();
-      dec_matmul<SL1>(xs, 0, w1, (nr + RG - 1) / RG, part, zs);
-      if (tid < nr * UPC) {
-        const int r = tid / UPC, uu = tid % UPC, b = row0 + r;
-        const float* zc = a.zc1 + ((size_t)b * N + t) * (4 * H) + c * UPC + uu;
-        float cc = cst[(MAX_ROWS + b) * UPC + uu];
-        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
-        cst[(MAX_ROWS + b) * UPC + uu] = cc;
-        a.h1[((size_t)cur * B + b) * H + c * UPC + uu] = h;
+    };
+    auto pass = [&](int tf, int ps) {        // 8 columns of mel_{tf}
+      pre_gemm8<16>(xs, PRE_KP, ps < 2 ? wos + (size_t)ps * WBLK : wg + (size_t)2 * WBLK, part, outv);
+      const int lc = ps * 8 + ocol;
+      if (orow < B && lc < 20) {
+        const int m = q * 20 + lc;
+        a.mel[((size_t)orow * N + tf) * vc::MEL + m] = outv[tid] + __ldg(a.bo + m);
       }
-      __syncthreads();
+    };
+    for (int t = 0; t < N; ++t) {
+      grid.sync();
+      grid.sync();
+      // output frame t-1, off the critical path: h_{t-1} stays intact until phase C of frame t+1
+      if (t > 0) { stage((t & 1) ^ 1); pass(t - 1, 0); }
+      grid.sync();
+      if (t > 0) { pass(t - 1, 1); pass(t - 1, 2); }
+      grid.sync();
     }
-    grid.sync();
+    stage((N - 1) & 1);
+    for (int ps = 0; ps < 3; ++ps) pass(N - 1, ps);
   }
+#undef DEC_MARK
+  if (a.dbg && tid == 0)
+    for (int i = 0; i < 8; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tm[i];
 }
 
 // Wc[i][o] = sum_m Wo[i][m] * W1[m][o]   (1024 x 80) . (80 x 256), double accumulation; bc = bo . W1
@@ -670,7 +774,11 @@ constexpr size_t enc_scan_smem() {
   return ((size_t)(vc::ENC_D + NSLICE) * NCOL + RG * (vc::ENC_D + 4) + 8 * RG * NCOL + RG * NCOL + MAX_ROWS * UPC) * 4;
 }
 constexpr size_t dec_scan_smem() {
-  return ((size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + DEC_XR * NCOL + 2 * MAX_ROWS * UPC + 2 * vc::DEC_H * 8 + vc::PRENET * 2) * 4;
+  constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + DEC_XR * NCOL + 2 * DEC_XR * UPC;
+  constexpr size_t pre = (size_t)32 * PRE_KP + 2 * (2 * vc::DEC_H + NSLICE) * 8 + 2 * (vc::PRENET + NSLICE) * 8 + 8 * 256 + 256;
+  constexpr size_t proj = (size_t)32 * PRE_KP + 2 * (2 * vc::DEC_H + NSLICE) * 8 + 8 * 256 + 256;
+  constexpr size_t m1 = lstm > pre ? lstm : pre;
+  return (m1 > proj ? m1 : proj) * 4;
 }
 
 // derived-weight slots (ctx->ac_d)
@@ -680,20 +788,23 @@ enum {
   D_ENC_WHR,     // [2][64][256][16]
   D_DEC_W0R,     // [128][768][16]
   D_DEC_W1R,     // [128][1280][16]
-  D_DEC_WC,      // [32][1024][8]  (Wo . W1) columns
+  D_DEC_WC,      // [16][1024][16]  (Wo . W1) columns
   D_DEC_WCFULL,  // [1024][256] scratch
   D_DEC_BC,      // [256]
   D_DEC_WP2,     // [128][256][2]
-  D_DEC_WO,      // [20][1024][4]
+  D_DEC_WO,      // [4][3][1088][8] (20 columns used per CTA)
   D_COUNT
 };
+
+// slots of ctx->ac_wpk_t (tensor-core packed weights)
+enum { WP_ENC = 0, WP_ENCH = 3, WP_DECH = 11, WP_POST0 = 27, WP_POST1 = 29, WP_POST2 = 31, WP_POST3 = 33, WP_POST4 = 35, WP_COUNT = 36 };
 
 }  // namespace
 
 int vtts_acoustic_prepare(vtts_ctx* ctx) {
   const size_t sizes[D_COUNT] = {256, 256, 256, 512, 512, 512, 512,
                                  (size_t)2 * 64 * 256 * 16, (size_t)128 * 768 * 16, (size_t)128 * 1280 * 16,
-                                 (size_t)128 * 1024 * 2, (size_t)1024 * 256, 256, (size_t)128 * 256 * 2, (size_t)80 * 1024};
+                                 (size_t)16 * 1024 * 16, (size_t)1024 * 256, 256, (size_t)16 * 256 * 16, (size_t)4 * 3 * 1088 * 8};
   size_t total = 0;
   std::vector<size_t> offs(D_COUNT);
   for (int i = 0; i < D_COUNT; ++i) {
@@ -714,10 +825,33 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
   repack_cols_kernel<<<512, 256>>>(T[aci::DEC_L0_W], 2048, 512, 768, ctx->ac_d[D_DEC_W0R], 128, 16, UPC, 512);
   repack_cols_kernel<<<512, 256>>>(T[aci::DEC_L1_W], 2048, 512, 1280, ctx->ac_d[D_DEC_W1R], 128, 16, UPC, 512);
   precompose_kernel<<<2 * vc::DEC_H + 1, 256>>>(T[aci::PROJ_W], T[aci::PROJ_B], T[aci::PRE1_W], ctx->ac_d[D_DEC_WCFULL], ctx->ac_d[D_DEC_BC]);
-  repack_cols_kernel<<<256, 256>>>(ctx->ac_d[D_DEC_WCFULL], 256, 0, 1024, ctx->ac_d[D_DEC_WC], 32, 8, 8, 0);
-  repack_cols_kernel<<<64, 256>>>(T[aci::PRE2_W], 256, 0, 256, ctx->ac_d[D_DEC_WP2], 128, 2, 2, 0);
-  repack_cols_kernel<<<64, 256>>>(T[aci::PROJ_W], 80, 0, 1024, ctx->ac_d[D_DEC_WO], 20, 4, 4, 0);
+  repack_cols_kernel<<<256, 256>>>(ctx->ac_d[D_DEC_WCFULL], 256, 0, 1024, ctx->ac_d[D_DEC_WC], 16, 16, 16, 0);
+  repack_cols_kernel<<<64, 256>>>(T[aci::PRE2_W], 256, 0, 256, ctx->ac_d[D_DEC_WP2], 16, 16, 16, 0);
+  VTTS_CUDA(cudaMemset(ctx->ac_d[D_DEC_WO], 0, (size_t)4 * 3 * 1088 * 8 * sizeof(float)));
+  repack_proj_kernel<<<64, 256>>>(T[aci::PROJ_W], ctx->ac_d[D_DEC_WO]);
   VTTS_CUDA(cudaGetLastError());
+  // ---- tensor-core packed weights of the convs and hoisted GEMMs ----
+  {
+    size_t bytes = 3 * vtts_tc_conv_packed_bytes(3, 256, 256) + 2 * vtts_tc_conv_packed_bytes(1, 256, 1024) +
+                   2 * vtts_tc_conv_packed_bytes(1, 512, 2048) + vtts_tc_conv_packed_bytes(5, 80, 512) +
+                   3 * vtts_tc_conv_packed_bytes(5, 512, 512) + vtts_tc_conv_packed_bytes(5, 512, 80);
+    if (ctx->ac_wpk) cudaFree(ctx->ac_wpk);
+    VTTS_CUDA(cudaMalloc(&ctx->ac_wpk, bytes));
+    char* cur = (char*)ctx->ac_wpk;
+    ctx->ac_wpk_t.clear();
+    int rc = 0;
+    for (int i = 0; i < 3 && !rc; ++i) rc = vtts_tc_pack_conv(ctx, T[aci::ENC_CONV(i, 0)], 3, 256, 256, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::ENC_LSTM_F_W], 1, 256, 1024, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::ENC_LSTM_B_W], 1, 256, 1024, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::DEC_L0_W], 1, 512, 2048, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::DEC_L1_W], 1, 512, 2048, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(0, 0)], 5, 80, 512, cur, ctx->ac_wpk_t);
+    for (int i = 1; i < 4 && !rc; ++i) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(i, 0)], 5, 512, 512, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(4, 0)], 5, 512, 80, cur, ctx->ac_wpk_t);
+    if (rc) return rc;
+    if ((int)ctx->ac_wpk_t.size() != WP_COUNT || (size_t)(cur - (char*)ctx->ac_wpk) > bytes)
+      return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: packed weight table has %d entries", (int)ctx->ac_wpk_t.size());
+  }
   VTTS_CUDA(cudaDeviceSynchronize());
   VTTS_CUDA(cudaFuncSetAttribute(enc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_scan_smem()));
   VTTS_CUDA(cudaFuncSetAttribute(decoder_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_scan_smem()));
@@ -734,7 +868,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
       return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: B=%d L=%d N=%d (1 <= B <= %d rows per call; the host layer chunks larger batches)", B, L, N, MAX_ROWS);
     if (mode < 0 || mode > 2) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: dropout_mode %d", mode);
     if (mode == VTTS_DROPOUT_MASK && !keep) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: dropout_mode MASK needs keep_mask");
-    if (ctx->sm_count < SCAN_CTAS) return ctx->fail(VTTS_ERR_NO_DEVICE, "scan kernels need %d SMs, device has %d", SCAN_CTAS, ctx->sm_count);
+    if (ctx->sm_count < DEC_CTAS) return ctx->fail(VTTS_ERR_NO_DEVICE, "scan kernels need %d SMs, device has %d", DEC_CTAS, ctx->sm_count);
   }
   Arena ar(ws_base, ws_cap, measure);
   const size_t BL = (size_t)B * L, BN = (size_t)B * N;
@@ -779,7 +913,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     Lc.len = lengths; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 2;
     Lc.p[0] = ConvProb{cur, nullptr, nullptr, T[aci::ENC_CONV(i, 0)], T[aci::ENC_CONV(i, 1)], nullptr,
                        T[aci::ENC_CONV(i, 4)], D[D_ENC_BNINV0 + i], T[aci::ENC_CONV(i, 3)], nxt, 3, 1, -1, 1, 0};
-    int rc = vtts_launch_conv(ctx, Lc, st);
+    int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_ENC + i], st);
     if (rc) return rc;
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
@@ -791,7 +925,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   Lc.len = nullptr; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;
   Lc.p[0] = ConvProb{cur, nullptr, nullptr, T[aci::ENC_LSTM_F_W], T[aci::ENC_LSTM_F_B], nullptr, nullptr, nullptr, nullptr, zx, 1, 1, 0, 1, 0};
   Lc.p[1] = ConvProb{cur, nullptr, nullptr, T[aci::ENC_LSTM_B_W], T[aci::ENC_LSTM_B_B], nullptr, nullptr, nullptr, nullptr, zx + BL * 1024, 1, 1, 0, 1, 0};
-  int rc = vtts_launch_conv(ctx, Lc, st);
+  int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_ENCH], st);
   if (rc) return rc;
   // ---- BiLSTM scan ----
   {
@@ -817,19 +951,21 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0; Lc.len_mul = 1;
   Lc.p[0] = ConvProb{cond, nullptr, nullptr, T[aci::DEC_L0_W], T[aci::DEC_L0_B], nullptr, nullptr, nullptr, nullptr, zc0, 1, 1, 0, 1, 0};
   Lc.p[1] = ConvProb{cond, nullptr, nullptr, T[aci::DEC_L1_W], T[aci::DEC_L1_B], nullptr, nullptr, nullptr, nullptr, zc1, 1, 1, 0, 1, 0};
-  rc = vtts_launch_conv(ctx, Lc, st);
+  rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_DECH], st);
   if (rc) return rc;
-  // ---- autoregressive scan ----
-  {
+  // ---- autoregressive scan: launches of up to 32 rows (rows are independent) ----
+  for (int b0 = 0; b0 < B; b0 += DEC_XR) {
+    const int nb = B - b0 < DEC_XR ? B - b0 : DEC_XR;
     DecScanArgs da;
-    da.zc0 = zc0; da.zc1 = zc1;
+    memset(&da, 0, sizeof(da));
+    da.zc0 = zc0 + (size_t)b0 * N * 2048; da.zc1 = zc1 + (size_t)b0 * N * 2048;
     da.w0r = D[D_DEC_W0R]; da.w1r = D[D_DEC_W1R]; da.wc = D[D_DEC_WC]; da.bc = D[D_DEC_BC]; da.wp2 = D[D_DEC_WP2];
     da.wo = D[D_DEC_WO]; da.bo = T[aci::PROJ_B];
     da.keep = keep; da.seed = seed; da.mode = mode;
-    da.p1 = p1; da.p2 = p2; da.h0 = h0; da.h1 = h1; da.mel = melpre;
-    da.B = B; da.N = N;
+    da.p1 = p1; da.p2 = p2; da.h0 = h0; da.h1 = h1; da.mel = melpre + (size_t)b0 * N * 80;
+    da.B = nb; da.N = N; da.row_base = b0; da.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
     void* args[] = {&da};
-    VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(SCAN_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
+    VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(DEC_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
     ctx->launches++;
   }
   // ---- postnet: 4 x [conv k5, BN, tanh], conv k5, + residual ----
@@ -848,7 +984,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     if (i == 4) { p.resid = melpre; p.out = mel; } else { p.out = pout; }
     p.k = 5; p.dil = 1; p.in_off = -2; p.out_stride = 1; p.out_off = 0;
     Lc.p[0] = p;
-    rc = vtts_launch_conv(ctx, Lc, st);
+    rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[i == 0 ? WP_POST0 : (i == 1 ? WP_POST1 : (i == 2 ? WP_POST2 : (i == 3 ? WP_POST3 : WP_POST4)))], st);
     if (rc) return rc;
     pin = pout;
     pout = (pout == q0) ? q1 : q0;

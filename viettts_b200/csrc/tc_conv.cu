@@ -67,6 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     if (clock64() - t0 > SPIN_TIMEOUT) spin_fail(err, code);
   }
 }
+// wait and add the stalled cycles to a per-role counter (profiling aid, see vtts_debug_tc_stats)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > SPIN_TIMEOUT) spin_fail(err, code);
+  }
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
@@ -105,6 +114,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one elected lane of a fully converged warp (elect.sync): lets ptxas issue uniform-datapath
+// instructions (UTCHMMA, UTCBAR) without a per-thread waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float lrelu(float v, float s) { return v >= 0.f ? v : s * v; }
 
 // split 4 floats into packed bf16 hi / lo
@@ -126,9 +147,12 @@ struct TcCfg {
   static constexpr int RA = R + 64;           // allocated activation rows per stage (halo <= 50)
   static constexpr int A_STAGE = RA * 64;     // bytes: 2 planes x 2 k-halves x RA rows x 16 B
   static constexpr int W_STAGE = N * 64;      // bytes: 2 planes x 2 k-halves x N rows x 16 B
-  static constexpr int TMEM_COLS = MT * N;    // 512, 512, 256, 128
-  static constexpr int NBAR = 2 * NA + 2 * NW + 2;
-  static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_STAGE + NBAR * 8 + 16 + 1024;
+  static constexpr int NACC = (2 * MT * N <= 512) ? 2 : 1;   // accumulator sets in TMEM (double buffered when they fit)
+  static constexpr int TMEM_COLS = NACC * MT * N;            // 512, 512, 512, 256
+  static constexpr int NBAR = 2 * NA + 2 * NW + 2 * NACC;
+  static constexpr int EPI_PITCH = 144;                      // bytes per staged row: 32 floats + 16 B pad (conflict-free)
+  static constexpr int EPI_STAGE = 4 * 32 * EPI_PITCH;       // one 32-row slab per epilogue warp
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_STAGE + EPI_STAGE + NBAR * 8 + 16 + 1024;
 };
 
 template <int N>
@@ -138,23 +162,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_st = smem;
+  constexpr int NACC = Cfg::NACC;
   uint8_t* w_st = smem + NA * Cfg::A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_st + NW * Cfg::W_STAGE);
+  uint8_t* epi_st = w_st + NW * Cfg::W_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_st + Cfg::EPI_STAGE);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + NA;
   uint64_t* w_full = bars + 2 * NA;
   uint64_t* w_empty = bars + 2 * NA + NW;
-  uint64_t* tmem_full = bars + 2 * NA + 2 * NW;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_full = bars + 2 * NA + 2 * NW;          // [NACC]
+  uint64_t* tmem_empty = tmem_full + NACC;               // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NACC);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index broadcast from lane 0: provably warp-uniform, so role code can live on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
   if (warp == 5 && lane == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], NCONV); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -164,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int nprob = L.nprob;
   const int Cin = L.Cin;
@@ -191,60 +218,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
 
   if (warp == 4) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // The whole warp walks the pipeline (uniform control flow, operands in uniform registers); only the
+    // tcgen05.mma / tcgen05.commit instructions themselves are predicated on one elected lane.
+    {
       constexpr uint32_t idesc = make_idesc(N);
-      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, tph = 0;
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, acc = 0, tph = 0;
+      long long w_tmem = 0, w_a = 0, w_w = 0;
+      const long long t_begin = clock64();
+      const uint32_t a_st_u32 = smem_u32(a_st), w_st_u32 = smem_u32(w_st);
+      // descriptor templates: start address added per use (row stride 16 B == 1 descriptor address unit)
+      const uint64_t a_tmpl = make_desc(0, RA * 16, 128);
+      const uint64_t b_tmpl = make_desc(0, N * 16, 128);
       TILE_LOOP_BEGIN
         (void)b; (void)tau0;
         const int k = P.k, dil = P.dil;
-        mbar_wait(tmem_empty, tph ^ 1, L.err, 1);
+        mbar_wait_t(&tmem_empty[acc], tph ^ 1, L.err, 1, w_tmem);
         tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (MT * N);
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(&a_full[sa], pa, L.err, 2);
+          mbar_wait_t(&a_full[sa], pa, L.err, 2, w_a);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_st + sa * Cfg::A_STAGE);
+          const uint32_t a_base16 = (a_st_u32 + sa * Cfg::A_STAGE) >> 4;
           for (int j = 0; j < k; ++j) {
-            mbar_wait(&w_full[sw], pw, L.err, 3);
+            mbar_wait_t(&w_full[sw], pw, L.err, 3, w_w);
             tc_fence_after();
-            const uint32_t w_base = smem_u32(w_st + sw * Cfg::W_STAGE);
-            const uint64_t b_hi = make_desc(w_base, N * 16, 128);
-            const uint64_t b_lo = make_desc(w_base + 2 * N * 16, N * 16, 128);
+            const uint32_t w_base16 = (w_st_u32 + sw * Cfg::W_STAGE) >> 4;
+            const uint64_t b_hi = b_tmpl | (uint64_t)w_base16;
+            const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + 2 * N);
+            const uint32_t first = (c | j) != 0 ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint32_t row = mt * 128 + j * dil;
-              const uint64_t a_hi = make_desc(a_base + row * 16, RA * 16, 128);
-              const uint64_t a_lo = make_desc(a_base + 2 * RA * 16 + row * 16, RA * 16, 128);
-              const uint32_t d = tmem_base + mt * N;
-              umma(d, a_hi, b_hi, idesc, (c | j) != 0 ? 1u : 0u);
-              umma(d, a_hi, b_lo, idesc, 1u);
-              umma(d, a_lo, b_hi, idesc, 1u);
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t row = a_base16 + mt * 128 + j * dil;
+                const uint64_t a_hi = a_tmpl | (uint64_t)row;
+                const uint64_t a_lo = a_tmpl | (uint64_t)(row + 2 * RA);
+                const uint32_t d = d0 + mt * N;
+                umma(d, a_hi, b_hi, idesc, first);
+                umma(d, a_hi, b_lo, idesc, 1u);
+                umma(d, a_lo, b_hi, idesc, 1u);
+              }
+              umma_commit(&w_empty[sw]);
             }
-            umma_commit(&w_empty[sw]);
             if (++sw == NW) { sw = 0; pw ^= 1; }
           }
-          umma_commit(&a_empty[sa]);
+          if (elect_one()) umma_commit(&a_empty[sa]);
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(tmem_full);
-        tph ^= 1;
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        if (++acc == NACC) { acc = 0; tph ^= 1; }
       TILE_LOOP_END
+      if (L.dbg && lane == 0) {
+        long long* d = L.dbg + (size_t)blockIdx.x * 16;
+        d[0] = clock64() - t_begin; d[1] = w_tmem; d[2] = w_a; d[3] = w_w;
+      }
     }
     __syncwarp();
   } else if (warp == 5) {
     // ============================ weight producer ============================
     if (lane == 0) {
       uint32_t sw = 0, pw = 0;
+      long long w_e = 0;
       TILE_LOOP_BEGIN
         (void)b; (void)tau0;
         const int k = P.k;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk);
         for (int s = 0; s < nch * k; ++s) {
-          mbar_wait(&w_empty[sw], pw ^ 1, L.err, 4);
+          mbar_wait_t(&w_empty[sw], pw ^ 1, L.err, 4, w_e);
           mbar_expect_tx(&w_full[sw], Cfg::W_STAGE);
           bulk_g2s(w_st + sw * Cfg::W_STAGE, wsrc + (size_t)s * Cfg::W_STAGE, Cfg::W_STAGE, &w_full[sw]);
           if (++sw == NW) { sw = 0; pw ^= 1; }
         }
       TILE_LOOP_END
+      if (L.dbg) L.dbg[(size_t)blockIdx.x * 16 + 4] = w_e;
     }
     __syncwarp();
   } else if (warp >= 6) {
@@ -256,6 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     const float slope = L.pre_slope;
     const int ld = L.in_ld;
     uint32_t sa = 0, pa = 0;
+    long long w_ae = 0, t_fill = 0;
     TILE_LOOP_BEGIN
       const int k = P.k, dil = P.dil;
       const int rows = R + (k - 1) * dil;
@@ -265,7 +311,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       const float* x2 = pre_mode == 2 ? P.x2 + in_base : nullptr;
       const int row_base = tau0 + P.in_off;
       for (int c = 0; c < nch; ++c) {
-        mbar_wait(&a_empty[sa], pa ^ 1, L.err, 5);
+        mbar_wait_t(&a_empty[sa], pa ^ 1, L.err, 5, w_ae);
+        const long long tf0 = clock64();
         uint8_t* st = a_st + sa * Cfg::A_STAGE + ((q >> 1) * RA) * 16 + (q & 1) * 8;
         const int coff = c * 16 + q * 4;
         constexpr int U = 8;           // loads in flight per thread (memory-level parallelism)
@@ -306,52 +353,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
         }
         fence_proxy_async();
         mbar_arrive(&a_full[sa]);
+        t_fill += clock64() - tf0;
         if (++sa == NA) { sa = 0; pa ^= 1; }
       }
     TILE_LOOP_END
+    if (L.dbg && ct == 0) { L.dbg[(size_t)blockIdx.x * 16 + 5] = w_ae; L.dbg[(size_t)blockIdx.x * 16 + 6] = t_fill; }
   } else {
     // ============================ epilogue (warps 0-3) ============================
-    uint32_t tph = 0;
+    // TMEM -> registers (thread = row) -> per-warp padded smem slab -> registers (8 lanes = one 128 B row
+    // segment) so that the residual loads and the stores are fully coalesced; residuals of the next
+    // 32-column chunk are prefetched while the current one drains.
+    uint32_t acc = 0, tph = 0;
     const int out_ld = L.out_ld;
+    long long w_tf = 0, t_epi = 0;
+    uint8_t* slab = epi_st + warp * (32 * Cfg::EPI_PITCH);
+    const int trow = lane >> 3;          // 0..3   row inside a group of 4
+    const int tch = lane & 7;            // 16 B chunk inside the 128 B row segment
+    constexpr int NCHUNK = N / 32;
+    const int n_valid = L.n_valid > 0 ? L.n_valid : N;
+    const int post_act = L.post_act;
     TILE_LOOP_BEGIN
-      mbar_wait(tmem_full, tph, L.err, 6);
-      tc_fence_after();
       const size_t out_base = (size_t)b * L.rows_out * out_ld;
-#pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-        const int tau = tau0 + mt * 128 + warp * 32 + lane;
-        const bool ok = tau < valid;
-        const size_t orow = out_base + (size_t)(tau * P.out_stride + P.out_off) * out_ld;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + mt * N;
-#pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld16(taddr + c0 + 16, r + 16);
-          tmem_ld_wait();
-          if (ok) {
+      const int ostride = P.out_stride, ooff = P.out_off;
+      const float* __restrict__ resid = P.resid;
+      const int row_w = tau0 + warp * 32;          // first row of this warp inside M-tile 0
+      float4 rs[8];
+      auto load_resid = [&](int it, float4 (&dst)[8]) {
+        const int mt = it / NCHUNK, c0 = (it - mt * NCHUNK) * 32;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int n = c0 + g * 4;
-              const float4 bi = __ldg(reinterpret_cast<const float4*>(P.bias + n));
-              float4 o;
-              o.x = __uint_as_float(r[g * 4 + 0]) + bi.x;
-              o.y = __uint_as_float(r[g * 4 + 1]) + bi.y;
-              o.z = __uint_as_float(r[g * 4 + 2]) + bi.z;
-              o.w = __uint_as_float(r[g * 4 + 3]) + bi.w;
-              if (P.resid) {
-                const float4 rs = __ldg(reinterpret_cast<const float4*>(P.resid + orow + n));
-                o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
-              }
-              *reinterpret_cast<float4*>(P.out + orow + n) = o;
-            }
+        for (int s8 = 0; s8 < 8; ++s8) {
+          const int tau = row_w + mt * 128 + s8 * 4 + trow;
+          dst[s8] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (resid && tau < valid && c0 + tch * 4 < n_valid)
+            dst[s8] = __ldg(reinterpret_cast<const float4*>(resid + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4));
+        }
+      };
+      load_resid(0, rs);
+      mbar_wait_t(&tmem_full[acc], tph, L.err, 6, w_tf);
+      const long long te0 = clock64();
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (MT * N);
+#pragma unroll 1
+      for (int it = 0; it < MT * NCHUNK; ++it) {
+        const int mt = it / NCHUNK, c0 = (it - mt * NCHUNK) * 32;
+        uint32_t r[32];
+        tmem_ld16(taddr0 + mt * N + c0, r);
+        tmem_ld16(taddr0 + mt * N + c0 + 16, r + 16);
+        float4 rs_next[8];
+        if (it + 1 < MT * NCHUNK) load_resid(it + 1, rs_next);
+        const bool col_ok = c0 + tch * 4 < n_valid;
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), mu = bi, iv = make_float4(1.f, 1.f, 1.f, 1.f), of = bi;
+        if (col_ok) {
+          bi = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + tch * 4));
+          if (P.bn_mean) {
+            mu = __ldg(reinterpret_cast<const float4*>(P.bn_mean + c0 + tch * 4));
+            iv = __ldg(reinterpret_cast<const float4*>(P.bn_inv + c0 + tch * 4));
+            of = __ldg(reinterpret_cast<const float4*>(P.bn_off + c0 + tch * 4));
           }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(slab + lane * Cfg::EPI_PITCH + q * 16) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+          const int rl = s8 * 4 + trow;
+          const int tau = row_w + mt * 128 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(slab + rl * Cfg::EPI_PITCH + tch * 16);
+          float4 o;
+          o.x = a.x + bi.x; o.y = a.y + bi.y; o.z = a.z + bi.z; o.w = a.w + bi.w;
+          if (P.bn_mean) {
+            o.x = (o.x - mu.x) * iv.x + of.x; o.y = (o.y - mu.y) * iv.y + of.y;
+            o.z = (o.z - mu.z) * iv.z + of.z; o.w = (o.w - mu.w) * iv.w + of.w;
+          }
+          if (post_act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+          else if (post_act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          o.x += rs[s8].x; o.y += rs[s8].y; o.z += rs[s8].z; o.w += rs[s8].w;
+          if (tau < valid && col_ok)
+            *reinterpret_cast<float4*>(P.out + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4) = o;
+        }
+        __syncwarp();
+        if (it + 1 < MT * NCHUNK) {
+#pragma unroll
+          for (int s8 = 0; s8 < 8; ++s8) rs[s8] = rs_next[s8];
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty);
-      tph ^= 1;
+      mbar_arrive(&tmem_empty[acc]);
+      t_epi += clock64() - te0;
+      if (++acc == NACC) { acc = 0; tph ^= 1; }
     TILE_LOOP_END
+    if (L.dbg && tid == 0) { L.dbg[(size_t)blockIdx.x * 16 + 7] = w_tf; L.dbg[(size_t)blockIdx.x * 16 + 8] = t_epi; }
   }
 #undef TILE_LOOP_BEGIN
 #undef TILE_LOOP_END
@@ -372,7 +465,7 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
     const int n = idx % N;
     const int i = (idx / N) % Cin;
     const int j = idx / ((size_t)N * Cin);
-    const float v = w[((size_t)j * Cin + i) * Cout_total + n0 + n];
+    const float v = (n0 + n) < Cout_total ? w[((size_t)j * Cin + i) * Cout_total + n0 + n] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const int c = i / 16, kh = (i % 16) / 8, e = i % 8;
@@ -409,12 +502,79 @@ int vtts_tc_pack_weights(vtts_ctx* ctx, const float* w, void* dst, int k, int Ci
   return VTTS_OK;
 }
 
+int vtts_tc_tile_n(int Cout) { return Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256)); }
+
+size_t vtts_tc_conv_packed_bytes(int k, int Cin, int Cout) {
+  const int N = vtts_tc_tile_n(Cout), nt = (Cout + N - 1) / N;
+  return ((vtts_tc_packed_elems(k, Cin, N) * 2 + 255) & ~size_t(255)) * nt;
+}
+
+int vtts_tc_pack_conv(vtts_ctx* ctx, const float* w, int k, int Cin, int Cout, char*& cursor, std::vector<void*>& out) {
+  const int N = vtts_tc_tile_n(Cout), nt = (Cout + N - 1) / N;
+  for (int t = 0; t < nt; ++t) {
+    int rc = vtts_tc_pack_weights(ctx, w, cursor, k, Cin, Cout, t * N, N);
+    if (rc) return rc;
+    out.push_back(cursor);
+    cursor += (vtts_tc_packed_elems(k, Cin, N) * 2 + 255) & ~size_t(255);
+  }
+  return VTTS_OK;
+}
+
+int vtts_conv_dispatch(vtts_ctx* ctx, const ConvLaunch& L, void* const* wpk, cudaStream_t st) {
+  if (ctx->precision != 1 || wpk == nullptr) return vtts_launch_conv(ctx, L, st);
+  const int N = vtts_tc_tile_n(L.Cout), nt = (L.Cout + N - 1) / N;
+  TcLaunch TL;
+  auto reset = [&]() {
+    memset(&TL, 0, sizeof(TL));
+    TL.Cin = L.Cin; TL.N = N; TL.in_ld = L.Cin; TL.out_ld = L.Cout; TL.B = L.B; TL.T_rows = L.T_rows; TL.rows_out = L.rows_out;
+    TL.len = L.len; TL.len_mul = L.len_mul; TL.pre_mode = L.pre_mode; TL.pre_slope = L.pre_slope; TL.post_act = L.post_act;
+    TL.n_valid = (L.Cout % N) ? (L.Cout % N) : N;   // only meaningful when nt == 1 or for the last tile (handled below)
+  };
+  reset();
+  // tiles that are completely valid and a partial last tile need different n_valid -> separate launches
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool partial = pass == 1;
+    if (partial && (L.Cout % N) == 0) break;
+    reset();
+    TL.n_valid = partial ? (L.Cout % N) : N;
+    for (int pi = 0; pi < L.nprob; ++pi) {
+      const ConvProb& cp = L.p[pi];
+      for (int t = 0; t < nt; ++t) {
+        const bool is_partial = (t == nt - 1) && (L.Cout % N) != 0;
+        if (is_partial != partial) continue;
+        const int n0 = t * N;
+        TcProb q;
+        memset(&q, 0, sizeof(q));
+        q.x0 = cp.x0; q.x1 = cp.x1; q.x2 = cp.x2;
+        q.wpk = wpk[pi * nt + t];
+        q.bias = cp.bias + n0;
+        q.resid = cp.resid ? cp.resid + n0 : nullptr;
+        if (cp.bn_mean) { q.bn_mean = cp.bn_mean + n0; q.bn_inv = cp.bn_inv + n0; q.bn_off = cp.bn_off + n0; }
+        q.out = cp.out + n0;
+        q.k = cp.k; q.dil = cp.dil; q.in_off = cp.in_off; q.out_stride = cp.out_stride; q.out_off = cp.out_off;
+        TL.p[TL.nprob++] = q;
+        if (TL.nprob == 8) {
+          int rc = vtts_launch_tc_conv(ctx, TL, st);
+          if (rc) return rc;
+          TL.nprob = 0;
+        }
+      }
+    }
+    if (TL.nprob > 0) {
+      int rc = vtts_launch_tc_conv(ctx, TL, st);
+      if (rc) return rc;
+    }
+  }
+  return VTTS_OK;
+}
+
 int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   if (L.nprob < 1 || L.nprob > 8) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: nprob %d", L.nprob);
   if (L.Cin % 16 != 0) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: Cin %d", L.Cin);
   for (int i = 0; i < L.nprob; ++i)
     if ((L.p[i].k - 1) * L.p[i].dil > 50 || L.p[i].k < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: halo too large");
   L.err = ctx->d_err;
+  L.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
   switch (L.N) {
     case 256: return launch_n<256>(ctx, L, st);
     case 128: return launch_n<128>(ctx, L, st);

@@ -76,6 +76,9 @@ struct TcProb {
   const void* wpk;       // packed bf16 hi/lo weights (vtts_tc_pack_weights)
   const float* bias;     // [N]
   const float* resid;    // rows_out x out_ld or null
+  const float* bn_mean;  // eval BatchNorm (all three or none), applied after the bias
+  const float* bn_inv;
+  const float* bn_off;
   float* out;
   int k, dil, in_off, out_stride, out_off;
 };
@@ -90,14 +93,19 @@ struct TcLaunch {
   int len_mul;
   int pre_mode;
   float pre_slope;
+  int post_act;          // 0 none, 1 tanh, 2 relu (after BN, before the residual)
+  int n_valid;           // real output channels of this N tile (<= N); 0 means N
   int tiles_per_row, ntiles;  // filled by the launcher
   int* err;                   // device int: set before trapping on a barrier timeout
+  long long* dbg;             // optional [grid][16] per-role stall counters (vtts_debug_tc_stats)
 };
 
 struct vtts_ctx {
   int device = 0;
   int precision = 1;            // 0 = strict fp32 (FMA pipe), 1 = bf16x3 on tcgen05 tensor cores (default)
   int* d_err = nullptr;
+  long long* d_tc_dbg = nullptr;   // [256][16] profiling counters of the last tensor-core conv launch
+  bool tc_dbg_on = false;
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
   std::vector<void*> hg_wpk_ups;   // [stage][phase] packed transposed-conv phase weights
@@ -117,6 +125,8 @@ struct vtts_ctx {
 
   float* ac_blob = nullptr;
   std::vector<float*> ac_t;
+  void* ac_wpk = nullptr;       // packed tensor-core weights of the acoustic model's convs / hoisted GEMMs
+  std::vector<void*> ac_wpk_t;
   float* ac_derived = nullptr;  // bn inv, repacked recurrent weights, ...
   std::vector<float*> ac_d;
   bool ac_loaded = false;
@@ -177,6 +187,13 @@ int vtts_launch_conv(vtts_ctx* ctx, const ConvLaunch& L, cudaStream_t st);
 size_t vtts_tc_packed_elems(int k, int Cin, int N);
 int vtts_tc_pack_weights(vtts_ctx* ctx, const float* w, void* dst, int k, int Cin, int Cout_total, int n0, int N);
 int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st);
+// generic dispatch: runs `L` on the tensor-core path when ctx->precision == 1 and packed weights are given
+// (wpk[prob * ntile + tile], ntile = ceil(Cout/256) tiles of width vtts_tc_tile_n(Cout)), else on the FP32 path
+int vtts_tc_tile_n(int Cout);
+int vtts_conv_dispatch(vtts_ctx* ctx, const ConvLaunch& L, void* const* wpk, cudaStream_t st);
+// packs every N tile of one conv weight; returns the number of tiles, appends device pointers to `out`
+int vtts_tc_pack_conv(vtts_ctx* ctx, const float* w, int k, int Cin, int Cout, char*& cursor, std::vector<void*>& out);
+size_t vtts_tc_conv_packed_bytes(int k, int Cin, int Cout);
 // hifigan.cu
 int vtts_hifigan_prepare(vtts_ctx* ctx);   // derived weights after load
 int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav, cudaStream_t st);

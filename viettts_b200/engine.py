@@ -92,6 +92,12 @@ class Engine:
                                             B, T, Cin, Cout, int(k), int(dil), float(pre_slope), _ptr(out)))
         return out
 
+    def tc_stats(self, enable=True):
+        """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats)."""
+        out = np.zeros((256, 16), np.int64)
+        self._ck(self.lib.vtts_debug_tc_stats(self.h, 1 if enable else 0, _ptr(out)))
+        return out
+
     # ---- weights ----
     def load_hifigan(self, params, key=None):
         """params: Haiku-layout dict, a packed float32 numpy blob, or a torch CUDA
