@@ -155,7 +155,9 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_STAGE + EPI_STAGE + NBAR * 8 + 16 + 1024;
 };
 
-template <int N>
+// EPI = 0: bias (+ residual) only -- the HiFiGAN generator's hot path.  EPI = 1: bias, eval BatchNorm,
+// tanh / relu, residual, partial N tile (acoustic model convs and GEMMs).
+template <int N, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_constant__ TcLaunch L) {
   using Cfg = TcCfg<N>;
   constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA;
@@ -370,8 +372,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     const int trow = lane >> 3;          // 0..3   row inside a group of 4
     const int tch = lane & 7;            // 16 B chunk inside the 128 B row segment
     constexpr int NCHUNK = N / 32;
-    const int n_valid = L.n_valid > 0 ? L.n_valid : N;
-    const int post_act = L.post_act;
+    const int n_valid = (EPI && L.n_valid > 0) ? L.n_valid : N;
+    const int post_act = EPI ? L.post_act : 0;
     TILE_LOOP_BEGIN
       const size_t out_base = (size_t)b * L.rows_out * out_ld;
       const int ostride = P.out_stride, ooff = P.out_off;
@@ -401,11 +403,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
         tmem_ld16(taddr0 + mt * N + c0 + 16, r + 16);
         float4 rs_next[8];
         if (it + 1 < MT * NCHUNK) load_resid(it + 1, rs_next);
-        const bool col_ok = c0 + tch * 4 < n_valid;
+        const bool col_ok = !EPI || (c0 + tch * 4 < n_valid);
         float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), mu = bi, iv = make_float4(1.f, 1.f, 1.f, 1.f), of = bi;
         if (col_ok) {
           bi = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + tch * 4));
-          if (P.bn_mean) {
+          if (EPI && P.bn_mean) {
             mu = __ldg(reinterpret_cast<const float4*>(P.bn_mean + c0 + tch * 4));
             iv = __ldg(reinterpret_cast<const float4*>(P.bn_inv + c0 + tch * 4));
             of = __ldg(reinterpret_cast<const float4*>(P.bn_off + c0 + tch * 4));
@@ -423,12 +425,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
           const float4 a = *reinterpret_cast<const float4*>(slab + rl * Cfg::EPI_PITCH + tch * 16);
           float4 o;
           o.x = a.x + bi.x; o.y = a.y + bi.y; o.z = a.z + bi.z; o.w = a.w + bi.w;
-          if (P.bn_mean) {
+          if (EPI && P.bn_mean) {
             o.x = (o.x - mu.x) * iv.x + of.x; o.y = (o.y - mu.y) * iv.y + of.y;
             o.z = (o.z - mu.z) * iv.z + of.z; o.w = (o.w - mu.w) * iv.w + of.w;
           }
-          if (post_act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-          else if (post_act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (EPI && post_act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+          else if (EPI && post_act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           o.x += rs[s8].x; o.y += rs[s8].y; o.z += rs[s8].z; o.w += rs[s8].w;
           if (tau < valid && col_ok)
             *reinterpret_cast<float4*>(P.out + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4) = o;
@@ -475,21 +477,28 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
-template <int N>
-int launch_n(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
+template <int N, int EPI>
+int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   using Cfg = TcCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
-    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   L.tiles_per_row = (L.T_rows + Cfg::R - 1) / Cfg::R;
   L.ntiles = L.nprob * L.tiles_per_row * L.B;
   const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
-  tc_conv_kernel<N><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  tc_conv_kernel<N, EPI><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
   ctx->launches++;
   VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
+}
+
+template <int N>
+int launch_n(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
+  bool generic = L.post_act != 0 || (L.n_valid > 0 && L.n_valid < N);
+  for (int i = 0; i < L.nprob; ++i) generic |= L.p[i].bn_mean != nullptr;
+  return generic ? launch_ne<N, 1>(ctx, L, st) : launch_ne<N, 0>(ctx, L, st);
 }
 
 }  // namespace
