@@ -274,7 +274,8 @@ int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16) {
   VTTS_CUDA(cudaDeviceSynchronize());
   if (host_out_256x16) VTTS_CUDA(cudaMemcpy(host_out_256x16, ctx->d_tc_dbg, 256 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   VTTS_CUDA(cudaMemset(ctx->d_tc_dbg, 0, 256 * 16 * sizeof(long long)));
-  ctx->tc_dbg_on = enable != 0;
+  ctx->tc_dbg_on = (enable & 1) != 0;
+  if (enable & 0x100) ctx->tc_variant = (enable >> 4) & 0xF;   // bit 8 set: bits 4..7 select the tile-shape variant (tuning aid)
   return VTTS_OK;
 }
 

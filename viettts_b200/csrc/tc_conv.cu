@@ -140,9 +140,13 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
   lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
 }
 
-template <int N>
+// V = 0: largest super tile (MT = min(4, 512/N)), accumulators double buffered only when they fit.
+// V = 1: half-size super tile for N >= 128 so that two accumulator sets fit (epilogue overlaps the next
+//        tile's MMAs; every weight stage then feeds half as many MMAs).
+template <int N, int V>
 struct TcCfg {
-  static constexpr int MT = (512 / N) < 4 ? (512 / N) : 4;
+  static constexpr int MT0 = (512 / N) < 4 ? (512 / N) : 4;
+  static constexpr int MT = (V == 1 && N >= 128) ? MT0 / 2 : MT0;
   static constexpr int R = 128 * MT;          // output rows per super tile
   static constexpr int RA = R + 64;           // allocated activation rows per stage (halo <= 50)
   static constexpr int A_STAGE = RA * 64;     // bytes: 2 planes x 2 k-halves x RA rows x 16 B
@@ -157,9 +161,9 @@ struct TcCfg {
 
 // EPI = 0: bias (+ residual) only -- the HiFiGAN generator's hot path.  EPI = 1: bias, eval BatchNorm,
 // tanh / relu, residual, partial N tile (acoustic model convs and GEMMs).
-template <int N, int EPI>
+template <int N, int EPI, int V>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_constant__ TcLaunch L) {
-  using Cfg = TcCfg<N>;
+  using Cfg = TcCfg<N, V>;
   constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -477,21 +481,29 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
-template <int N, int EPI>
-int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
-  using Cfg = TcCfg<N>;
+template <int N, int EPI, int V>
+int launch_nev(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
+  using Cfg = TcCfg<N, V>;
   static bool attr_done = false;
   if (!attr_done) {
-    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   L.tiles_per_row = (L.T_rows + Cfg::R - 1) / Cfg::R;
   L.ntiles = L.nprob * L.tiles_per_row * L.B;
   const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
-  tc_conv_kernel<N, EPI><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  tc_conv_kernel<N, EPI, V><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
   ctx->launches++;
   VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
+}
+
+template <int N, int EPI>
+int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
+  if constexpr (N >= 128) {
+    if (ctx->tc_variant == 1) return launch_nev<N, EPI, 1>(ctx, L, st);
+  }
+  return launch_nev<N, EPI, 0>(ctx, L, st);
 }
 
 template <int N>

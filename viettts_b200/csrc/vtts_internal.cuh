@@ -106,6 +106,7 @@ struct vtts_ctx {
   int* d_err = nullptr;
   long long* d_tc_dbg = nullptr;   // [256][16] profiling counters of the last tensor-core conv launch
   bool tc_dbg_on = false;
+  int tc_variant = 1;              // tile-shape variant of the tensor-core conv (see TcCfg); 1 = double-buffered accumulators for N >= 128
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
   std::vector<void*> hg_wpk_ups;   // [stage][phase] packed transposed-conv phase weights

@@ -92,10 +92,12 @@ class Engine:
                                             B, T, Cin, Cout, int(k), int(dil), float(pre_slope), _ptr(out)))
         return out
 
-    def tc_stats(self, enable=True):
-        """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats)."""
+    def tc_stats(self, enable=True, variant=None):
+        """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats);
+        `variant` (0/1) optionally selects the tile-shape variant for later launches."""
         out = np.zeros((256, 16), np.int64)
-        self._ck(self.lib.vtts_debug_tc_stats(self.h, 1 if enable else 0, _ptr(out)))
+        flags = (1 if enable else 0) | (0 if variant is None else (0x100 | (int(variant) << 4)))
+        self._ck(self.lib.vtts_debug_tc_stats(self.h, flags, _ptr(out)))
         return out
 
     # ---- weights ----
