@@ -318,6 +318,14 @@ def run_ours(args):
         frames = int(nfs.sum())
         flops = frames * C.HIFIGAN_FLOP_PER_FRAME
         ach = flops / (hg_ms / 1e3) / 1e12
+        traffic = None
+        tp = REPO / "profiles" / "r1_traffic.json"
+        if tp.exists():
+            tj = json.loads(tp.read_text())
+            w = tj.get("workload", {})
+            if w.get("batch") == B and w.get("mel_frames") == N and w.get("precision") == args.precision:
+                traffic = tj["generator_dram_bytes_per_step"]
+        ceiling = pk["bf16_tflops_sustained"] / 3.0 if args.precision != "fp32" else 74.4
         out = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
             higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -330,8 +338,15 @@ def run_ours(args):
             e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt / args.steps,
                      api="vtts_synthesize_host via viettts_b200.Engine.synthesize (numpy in, numpy out)"),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="HiFiGAN generator stage (conv1d_nwc_kernel launches + conv_post)", achieved=ach,
-                          peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_tflops_sustained"], traffic=None,
+            roofline=dict(bound="tensor",
+                          kernel=("tc_conv_kernel: the 29 generator launches of one step (+ conv_post, 1 % of the stage time)" if args.precision != "fp32"
+                                  else "conv1d_nwc_kernel: the 29 generator launches of one step (+ conv_post)"),
+                          achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_tflops_sustained"],
+                          traffic=traffic, traffic_unit="bytes of DRAM traffic per step, all launches of the kernel (ncu, profiles/r1_traffic.json)",
+                          algorithmic_flops_per_step=flops, launch_ms=hg_ms,
+                          frac_of_mode_ceiling=ach / ceiling,
+                          mode_ceiling=("1/3 of the bf16 peak: bf16x3 issues three bf16 MMAs per algorithmic product" if args.precision != "fp32"
+                                        else "FP32 FMA pipe, nominal 74.4 TFLOP/s"),
                           peak_source=pk["source"] + ", sustained bf16 dense",
                           note=("algorithmic fp32 FLOPs; the bf16x3 path issues 3 bf16 MMAs per algorithmic product, so 1/3 of the bf16 peak is its ceiling"
                                 if args.precision != "fp32" else "strict-fp32 path runs on the FP32 FMA pipe (nominal 74 TFLOP/s)")),

@@ -250,14 +250,28 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
       L.p[r] = p;
     }
     if (tc) {
+      // ConvTranspose phases share their input: for N <= 128 one converted activation tile feeds NPH phases
+      // (multi-phase tiles of tc_conv.cu); N = 256 keeps one problem per phase.
+      const int nph = Co == 256 ? 1 : (Co == 128 ? 4 : 2);
       TcLaunch TL;
       memset(&TL, 0, sizeof(TL));
-      TL.nprob = u; TL.Cin = C; TL.N = Co; TL.in_ld = C; TL.out_ld = Co;
+      TL.nprob = u / nph; TL.nphase = nph; TL.Cin = C; TL.N = Co; TL.in_ld = C; TL.out_ld = Co;
       TL.B = B; TL.T_rows = rows_in; TL.rows_out = rows_in * u; TL.len = n_frames; TL.len_mul = scale_in;
       TL.pre_mode = L.pre_mode; TL.pre_slope = 0.1f;
-      for (int r = 0; r < u; ++r) {
-        const ConvProb& cp = L.p[r];
-        TL.p[r] = TcProb{cp.x0, cp.x1, cp.x2, ctx->hg_wpk_ups[i * 8 + r], cp.bias, nullptr, nullptr, nullptr, nullptr, cp.out, 2, 1, cp.in_off, u, r};
+      for (int g = 0; g < u / nph; ++g) {
+        const ConvProb& c0 = L.p[g * nph];
+        TcProb q;
+        memset(&q, 0, sizeof(q));
+        q.x0 = c0.x0; q.x1 = c0.x1; q.x2 = c0.x2; q.bias = c0.bias; q.out = c0.out;
+        q.k = 2; q.dil = 1; q.out_stride = u;
+        q.wpk = ctx->hg_wpk_ups[i * 8 + g * nph]; q.in_off = c0.in_off; q.out_off = g * nph;
+        for (int ph = 0; ph < nph; ++ph) {
+          const int r = g * nph + ph;
+          q.wpk_ph[ph] = ctx->hg_wpk_ups[i * 8 + r];
+          q.in_off_ph[ph] = L.p[r].in_off;
+          q.out_off_ph[ph] = r;
+        }
+        TL.p[g] = q;
       }
       rc = vtts_launch_tc_conv(ctx, TL, st);
     } else {

@@ -24,14 +24,18 @@
 // weight block fetched from L2 feeds MT MMAs.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "vtts_internal.cuh"
 
 namespace {
 
-constexpr int NA = 3;               // activation stages
+constexpr int NA = 4;               // activation stages
 constexpr int NW = 4;               // weight stages
 constexpr int NTHREADS = 448;     // 4 epilogue + MMA + weight producer + 8 converter warps
 constexpr int NCONV = 256;        // converter threads
+constexpr int NGRP = 2;           // independent converter groups (alternate chunks -> two chunks in flight)
+constexpr int GRP_THREADS = NCONV / NGRP;
 constexpr long long SPIN_TIMEOUT = 4000000000LL;  // ~2 s of SM clocks: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,19 +144,22 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
   lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
 }
 
-// V = 0: largest super tile (MT = min(4, 512/N)), accumulators double buffered only when they fit.
-// V = 1: half-size super tile for N >= 128 so that two accumulator sets fit (epilogue overlaps the next
-//        tile's MMAs; every weight stage then feeds half as many MMAs).
-template <int N, int V>
+// MT  = M-tiles (128 rows) per super tile, NPH = output phases accumulated per tile (ConvTranspose), the
+// accumulator set of a tile is NPH*MT*N TMEM columns; two sets (epilogue overlaps the next tile's MMAs) when
+// they fit in the 512 columns.
+template <int N, int MT_, int NPH_>
 struct TcCfg {
-  static constexpr int MT0 = (512 / N) < 4 ? (512 / N) : 4;
-  static constexpr int MT = (V == 1 && N >= 128) ? MT0 / 2 : MT0;
+  static constexpr int MT = MT_;
+  static constexpr int NPH = NPH_;
   static constexpr int R = 128 * MT;          // output rows per super tile
   static constexpr int RA = R + 64;           // allocated activation rows per stage (halo <= 50)
   static constexpr int A_STAGE = RA * 64;     // bytes: 2 planes x 2 k-halves x RA rows x 16 B
   static constexpr int W_STAGE = N * 64;      // bytes: 2 planes x 2 k-halves x N rows x 16 B
-  static constexpr int NACC = (2 * MT * N <= 512) ? 2 : 1;   // accumulator sets in TMEM (double buffered when they fit)
-  static constexpr int TMEM_COLS = NACC * MT * N;            // 512, 512, 512, 256
+  static constexpr int ACC_COLS = NPH * MT * N;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_RAW = NACC * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : (TMEM_RAW <= 64 ? 64 : (TMEM_RAW <= 128 ? 128 : (TMEM_RAW <= 256 ? 256 : 512)));
   static constexpr int NBAR = 2 * NA + 2 * NW + 2 * NACC;
   static constexpr int EPI_PITCH = 144;                      // bytes per staged row: 32 floats + 16 B pad (conflict-free)
   static constexpr int EPI_STAGE = 4 * 32 * EPI_PITCH;       // one 32-row slab per epilogue warp
@@ -161,10 +168,10 @@ struct TcCfg {
 
 // EPI = 0: bias (+ residual) only -- the HiFiGAN generator's hot path.  EPI = 1: bias, eval BatchNorm,
 // tanh / relu, residual, partial N tile (acoustic model convs and GEMMs).
-template <int N, int EPI, int V>
+template <int N, int EPI, int MT_, int NPH_>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_constant__ TcLaunch L) {
-  using Cfg = TcCfg<N, V>;
-  constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA;
+  using Cfg = TcCfg<N, MT_, NPH_>;
+  constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA, NPH = Cfg::NPH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_st = smem;
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
   if (warp == 5 && lane == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], NCONV); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], GRP_THREADS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -219,7 +226,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       valid = v < valid ? v : valid;                                           \
     }                                                                          \
     if (tau0 >= valid) continue;                                               \
-    const TcProb& P = L.p[pi];
+    const TcProb& P = L.p[pi];                                                 \
+    int sh_min = P.in_off_ph[0], sh_max = P.in_off_ph[0];                      \
+    _Pragma("unroll") for (int ph_ = 1; ph_ < NPH; ++ph_) {                    \
+      sh_min = P.in_off_ph[ph_] < sh_min ? P.in_off_ph[ph_] : sh_min;          \
+      sh_max = P.in_off_ph[ph_] > sh_max ? P.in_off_ph[ph_] : sh_max;          \
+    }
 #define TILE_LOOP_END }
 
   if (warp == 4) {
@@ -240,32 +252,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
         const int k = P.k, dil = P.dil;
         mbar_wait_t(&tmem_empty[acc], tph ^ 1, L.err, 1, w_tmem);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * (MT * N);
+        const uint32_t d0 = tmem_base + acc * Cfg::ACC_COLS;
         for (int c = 0; c < nch; ++c) {
           mbar_wait_t(&a_full[sa], pa, L.err, 2, w_a);
           tc_fence_after();
           const uint32_t a_base16 = (a_st_u32 + sa * Cfg::A_STAGE) >> 4;
-          for (int j = 0; j < k; ++j) {
-            mbar_wait_t(&w_full[sw], pw, L.err, 3, w_w);
-            tc_fence_after();
-            const uint32_t w_base16 = (w_st_u32 + sw * Cfg::W_STAGE) >> 4;
-            const uint64_t b_hi = b_tmpl | (uint64_t)w_base16;
-            const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + 2 * N);
-            const uint32_t first = (c | j) != 0 ? 1u : 0u;
-            if (elect_one()) {
+#pragma unroll 1
+          for (int ph = 0; ph < NPH; ++ph) {
+            const int shift = P.in_off_ph[ph] - sh_min;
+            for (int j = 0; j < k; ++j) {
+              mbar_wait_t(&w_full[sw], pw, L.err, 3, w_w);
+              tc_fence_after();
+              const uint32_t w_base16 = (w_st_u32 + sw * Cfg::W_STAGE) >> 4;
+              const uint64_t b_hi = b_tmpl | (uint64_t)w_base16;
+              const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + 2 * N);
+              const uint32_t first = (c | j) != 0 ? 1u : 0u;
+              if (elect_one()) {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t row = a_base16 + mt * 128 + j * dil;
-                const uint64_t a_hi = a_tmpl | (uint64_t)row;
-                const uint64_t a_lo = a_tmpl | (uint64_t)(row + 2 * RA);
-                const uint32_t d = d0 + mt * N;
-                umma(d, a_hi, b_hi, idesc, first);
-                umma(d, a_hi, b_lo, idesc, 1u);
-                umma(d, a_lo, b_hi, idesc, 1u);
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t row = a_base16 + mt * 128 + shift + j * dil;
+                  const uint64_t a_hi = a_tmpl | (uint64_t)row;
+                  const uint64_t a_lo = a_tmpl | (uint64_t)(row + 2 * RA);
+                  const uint32_t d = d0 + (ph * MT + mt) * N;
+                  umma(d, a_hi, b_hi, idesc, first);
+                  umma(d, a_hi, b_lo, idesc, 1u);
+                  umma(d, a_lo, b_hi, idesc, 1u);
+                }
+                umma_commit(&w_empty[sw]);
               }
-              umma_commit(&w_empty[sw]);
+              if (++sw == NW) { sw = 0; pw ^= 1; }
             }
-            if (++sw == NW) { sw = 0; pw ^= 1; }
           }
           if (elect_one()) umma_commit(&a_empty[sa]);
           if (++sa == NA) { sa = 0; pa ^= 1; }
@@ -287,46 +303,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       TILE_LOOP_BEGIN
         (void)b; (void)tau0;
         const int k = P.k;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk);
-        for (int s = 0; s < nch * k; ++s) {
-          mbar_wait_t(&w_empty[sw], pw ^ 1, L.err, 4, w_e);
-          mbar_expect_tx(&w_full[sw], Cfg::W_STAGE);
-          bulk_g2s(w_st + sw * Cfg::W_STAGE, wsrc + (size_t)s * Cfg::W_STAGE, Cfg::W_STAGE, &w_full[sw]);
-          if (++sw == NW) { sw = 0; pw ^= 1; }
-        }
+        for (int c = 0; c < nch; ++c)
+          for (int ph = 0; ph < NPH; ++ph) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk_ph[ph]) + (size_t)c * k * Cfg::W_STAGE;
+            for (int j = 0; j < k; ++j) {
+              mbar_wait_t(&w_empty[sw], pw ^ 1, L.err, 4, w_e);
+              mbar_expect_tx(&w_full[sw], Cfg::W_STAGE);
+              bulk_g2s(w_st + sw * Cfg::W_STAGE, wsrc + (size_t)j * Cfg::W_STAGE, Cfg::W_STAGE, &w_full[sw]);
+              if (++sw == NW) { sw = 0; pw ^= 1; }
+            }
+          }
       TILE_LOOP_END
       if (L.dbg) L.dbg[(size_t)blockIdx.x * 16 + 4] = w_e;
     }
     __syncwarp();
   } else if (warp >= 6) {
     // ============================ activation converters ============================
-    const int ct = tid - 192;          // 0..255
-    const int q = ct & 3;              // 4-channel group inside the 16-channel chunk
-    const int r0 = ct >> 2;            // 0..63
+    // Two groups of 4 warps; group g fills the chunks with (global chunk counter) % 2 == g, so one group's
+    // memory round trip overlaps the other's convert+store phase.
+    const int ct = tid - 192;                 // 0..255
+    const int grp = ct / GRP_THREADS;         // 0..1
+    const int gt = ct - grp * GRP_THREADS;    // 0..127 inside the group
+    const int q = gt & 3;                     // 4-channel group inside the 16-channel chunk
+    const int r0 = gt >> 2;                   // 0..31
     const int pre_mode = L.pre_mode;
     const float slope = L.pre_slope;
     const int ld = L.in_ld;
-    uint32_t sa = 0, pa = 0;
+    uint32_t item = 0;                        // global chunk counter (same sequence in both groups and the MMA warp)
     long long w_ae = 0, t_fill = 0;
     TILE_LOOP_BEGIN
       const int k = P.k, dil = P.dil;
-      const int rows = R + (k - 1) * dil;
+      const int rows = R + (k - 1) * dil + (sh_max - sh_min);
       const size_t in_base = (size_t)b * L.T_rows * ld;
       const float* x0 = P.x0 + in_base;
       const float* x1 = pre_mode == 2 ? P.x1 + in_base : nullptr;
       const float* x2 = pre_mode == 2 ? P.x2 + in_base : nullptr;
-      const int row_base = tau0 + P.in_off;
-      for (int c = 0; c < nch; ++c) {
+      const int row_base = tau0 + sh_min;
+      for (int c = 0; c < nch; ++c, ++item) {
+        if ((int)(item % NGRP) != grp) continue;
+        const uint32_t sa = item % NA, pa = (item / NA) & 1;
         mbar_wait_t(&a_empty[sa], pa ^ 1, L.err, 5, w_ae);
         const long long tf0 = clock64();
         uint8_t* st = a_st + sa * Cfg::A_STAGE + ((q >> 1) * RA) * 16 + (q & 1) * 8;
         const int coff = c * 16 + q * 4;
-        constexpr int U = 8;           // loads in flight per thread (memory-level parallelism)
-        for (int rr0 = r0; rr0 < rows; rr0 += 64 * U) {
+        constexpr int U = 10;          // loads in flight per thread (memory-level parallelism)
+        for (int rr0 = r0; rr0 < rows; rr0 += 32 * U) {
           float4 v[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int rr = rr0 + u * 64;
+            const int rr = rr0 + u * 32;
             const int t = row_base + rr;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rr < rows && t >= 0 && t < valid) {
@@ -344,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int rr = rr0 + u * 64;
+            const int rr = rr0 + u * 32;
             if (rr < rows) {
               float4 x = v[u];
               if (pre_mode >= 1) {
@@ -360,10 +385,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
         fence_proxy_async();
         mbar_arrive(&a_full[sa]);
         t_fill += clock64() - tf0;
-        if (++sa == NA) { sa = 0; pa ^= 1; }
       }
     TILE_LOOP_END
-    if (L.dbg && ct == 0) { L.dbg[(size_t)blockIdx.x * 16 + 5] = w_ae; L.dbg[(size_t)blockIdx.x * 16 + 6] = t_fill; }
+    if (L.dbg && gt == 0) { L.dbg[(size_t)blockIdx.x * 16 + 5 + 4 * grp] = w_ae; L.dbg[(size_t)blockIdx.x * 16 + 6 + 4 * grp] = t_fill; }
   } else {
     // ============================ epilogue (warps 0-3) ============================
     // TMEM -> registers (thread = row) -> per-warp padded smem slab -> registers (8 lanes = one 128 B row
@@ -380,12 +404,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     const int post_act = EPI ? L.post_act : 0;
     TILE_LOOP_BEGIN
       const size_t out_base = (size_t)b * L.rows_out * out_ld;
-      const int ostride = P.out_stride, ooff = P.out_off;
+      const int ostride = P.out_stride;
       const float* __restrict__ resid = P.resid;
       const int row_w = tau0 + warp * 32;          // first row of this warp inside M-tile 0
       float4 rs[8];
       auto load_resid = [&](int it, float4 (&dst)[8]) {
-        const int mt = it / NCHUNK, c0 = (it - mt * NCHUNK) * 32;
+        const int pm = it / NCHUNK, c0 = (it - pm * NCHUNK) * 32;
+        const int mt = pm % MT, ooff = P.out_off_ph[pm / MT];
 #pragma unroll
         for (int s8 = 0; s8 < 8; ++s8) {
           const int tau = row_w + mt * 128 + s8 * 4 + trow;
@@ -398,15 +423,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       mbar_wait_t(&tmem_full[acc], tph, L.err, 6, w_tf);
       const long long te0 = clock64();
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (MT * N);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * Cfg::ACC_COLS;
 #pragma unroll 1
-      for (int it = 0; it < MT * NCHUNK; ++it) {
-        const int mt = it / NCHUNK, c0 = (it - mt * NCHUNK) * 32;
+      for (int it = 0; it < NPH * MT * NCHUNK; ++it) {
+        const int pm = it / NCHUNK, c0 = (it - pm * NCHUNK) * 32;
+        const int mt = pm % MT, ooff = P.out_off_ph[pm / MT];
         uint32_t r[32];
-        tmem_ld16(taddr0 + mt * N + c0, r);
-        tmem_ld16(taddr0 + mt * N + c0 + 16, r + 16);
+        tmem_ld16(taddr0 + pm * N + c0, r);
+        tmem_ld16(taddr0 + pm * N + c0 + 16, r + 16);
         float4 rs_next[8];
-        if (it + 1 < MT * NCHUNK) load_resid(it + 1, rs_next);
+        if (it + 1 < NPH * MT * NCHUNK) load_resid(it + 1, rs_next);
         const bool col_ok = !EPI || (c0 + tch * 4 < n_valid);
         float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), mu = bi, iv = make_float4(1.f, 1.f, 1.f, 1.f), of = bi;
         if (col_ok) {
@@ -440,7 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             *reinterpret_cast<float4*>(P.out + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4) = o;
         }
         __syncwarp();
-        if (it + 1 < MT * NCHUNK) {
+        if (it + 1 < NPH * MT * NCHUNK) {
 #pragma unroll
           for (int s8 = 0; s8 < 8; ++s8) rs[s8] = rs_next[s8];
         }
@@ -481,35 +507,64 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
-template <int N, int EPI, int V>
-int launch_nev(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
-  using Cfg = TcCfg<N, V>;
+template <int N, int EPI, int MT, int NPH>
+int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
+  using Cfg = TcCfg<N, MT, NPH>;
   static bool attr_done = false;
   if (!attr_done) {
-    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, MT, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
+  }
+  for (int i = 0; i < L.nprob; ++i) {
+    if (NPH == 1) {   // single-phase problems describe themselves with the scalar fields
+      L.p[i].wpk_ph[0] = L.p[i].wpk;
+      L.p[i].in_off_ph[0] = L.p[i].in_off;
+      L.p[i].out_off_ph[0] = L.p[i].out_off;
+    }
+    int mn = L.p[i].in_off_ph[0], mx = mn;
+    for (int ph = 1; ph < NPH; ++ph) { mn = std::min(mn, L.p[i].in_off_ph[ph]); mx = std::max(mx, L.p[i].in_off_ph[ph]); }
+    if ((L.p[i].k - 1) * L.p[i].dil + (mx - mn) > 50) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: halo too large");
   }
   L.tiles_per_row = (L.T_rows + Cfg::R - 1) / Cfg::R;
   L.ntiles = L.nprob * L.tiles_per_row * L.B;
   const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
-  tc_conv_kernel<N, EPI, V><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  tc_conv_kernel<N, EPI, MT, NPH><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
   ctx->launches++;
   VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
 }
 
+// tile shapes: single-phase: N=256 -> MT 1, N=128 -> MT 2 (two accumulator sets), N<=64 -> MT 4
+//              multi-phase (ConvTranspose): N=128 x 4 phases x MT 1, N=64 x 2 x MT 2, N=32 x 2 x MT 4
 template <int N, int EPI>
 int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
-  if constexpr (N >= 128) {
-    if (ctx->tc_variant == 1) return launch_nev<N, EPI, 1>(ctx, L, st);
+  const int nph = L.nphase > 1 ? L.nphase : 1;
+  if constexpr (N == 256) {
+    if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=256 supports single-phase tiles only");
+    if (ctx->tc_variant == 0) return launch_cfg<256, EPI, 2, 1>(ctx, L, st);
+    return launch_cfg<256, EPI, 1, 1>(ctx, L, st);
+  } else if constexpr (N == 128) {
+    if (nph == 4) return launch_cfg<128, EPI, 1, 4>(ctx, L, st);
+    if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=128 supports 1 or 4 phases");
+    if (ctx->tc_variant == 0) return launch_cfg<128, EPI, 4, 1>(ctx, L, st);
+    return launch_cfg<128, EPI, 2, 1>(ctx, L, st);
+  } else if constexpr (N == 64) {
+    if (nph == 2) return launch_cfg<64, EPI, 2, 2>(ctx, L, st);
+    if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=64 supports 1 or 2 phases");
+    return launch_cfg<64, EPI, 4, 1>(ctx, L, st);
+  } else {
+    if (nph == 2) return launch_cfg<32, EPI, 4, 2>(ctx, L, st);
+    if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=32 supports 1 or 2 phases");
+    return launch_cfg<32, EPI, 4, 1>(ctx, L, st);
   }
-  return launch_nev<N, EPI, 0>(ctx, L, st);
 }
 
 template <int N>
 int launch_n(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   bool generic = L.post_act != 0 || (L.n_valid > 0 && L.n_valid < N);
   for (int i = 0; i < L.nprob; ++i) generic |= L.p[i].bn_mean != nullptr;
+  if (L.nphase > 1 && !generic) return launch_ne<N, 0>(ctx, L, st);
+  if (L.nphase > 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: multi-phase tiles use the plain epilogue");
   return generic ? launch_ne<N, 1>(ctx, L, st) : launch_ne<N, 0>(ctx, L, st);
 }
 
@@ -593,7 +648,7 @@ int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   if (L.nprob < 1 || L.nprob > 8) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: nprob %d", L.nprob);
   if (L.Cin % 16 != 0) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: Cin %d", L.Cin);
   for (int i = 0; i < L.nprob; ++i)
-    if ((L.p[i].k - 1) * L.p[i].dil > 50 || L.p[i].k < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: halo too large");
+    if (L.p[i].k < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: k");
   L.err = ctx->d_err;
   L.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
   switch (L.N) {

@@ -81,6 +81,12 @@ struct TcProb {
   const float* bn_off;
   float* out;
   int k, dil, in_off, out_stride, out_off;
+  // multi-phase tiles (TcLaunch::nphase > 1): phase ph of this problem uses weights wpk_ph[ph], reads input rows
+  // shifted by in_off_ph[ph] and writes output rows tau*out_stride + out_off_ph[ph]; one converted activation
+  // tile feeds all phases (ConvTranspose output phases share their input)
+  const void* wpk_ph[4];
+  int in_off_ph[4];
+  int out_off_ph[4];
 };
 
 struct TcLaunch {
@@ -93,6 +99,7 @@ struct TcLaunch {
   int len_mul;
   int pre_mode;
   float pre_slope;
+  int nphase;            // phases per tile (1, 2 or 4); 0 means 1
   int post_act;          // 0 none, 1 tanh, 2 relu (after BN, before the residual)
   int n_valid;           // real output channels of this N tile (<= N); 0 means N
   int tiles_per_row, ntiles;  // filled by the launcher
