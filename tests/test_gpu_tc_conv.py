@@ -83,3 +83,46 @@ def test_generator_bf16x3_batch32_rows_independent(eng):
     assert np.isfinite(wav).all()
     alone = eng.mel2wave(mel[17:18])
     assert np.array_equal(alone[0], wav[17])
+
+
+def _ref_pair(x, w1, b1, w2, b2, k, dil, slope):
+    xt = torch.from_numpy(x).double()
+    f = torch.nn.functional
+    y = f.leaky_relu(xt, slope).transpose(1, 2)
+    y = f.conv1d(y, torch.from_numpy(w1).double().permute(2, 1, 0).contiguous(), torch.from_numpy(b1).double(), padding=(k - 1) * dil // 2, dilation=dil)
+    y = f.leaky_relu(y, slope)
+    y = f.conv1d(y, torch.from_numpy(w2).double().permute(2, 1, 0).contiguous(), torch.from_numpy(b2).double(), padding=(k - 1) // 2)
+    return (y.transpose(1, 2) + xt).numpy()
+
+
+@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("k,dil", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
+def test_fused_pair_vs_float64(eng, C, k, dil):
+    """Fused ResBlock pair (tc_pair.cu): row semantics (zero padding of BOTH convs at each row's true end)."""
+    rng = np.random.default_rng(C * 1000 + k * 10 + dil)
+    B, T = 3, 700
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    w1 = (rng.standard_normal((k, C, C)) / np.sqrt(k * C)).astype(np.float32)
+    w2 = (rng.standard_normal((k, C, C)) / np.sqrt(k * C)).astype(np.float32)
+    b1 = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    b2 = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    lens = np.array([T, 257, 3], np.int32)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    out = eng.debug_pair(t(x), t(w1), t(b1), t(w2), t(b2), k, dil, 0.1, t(lens)).cpu().numpy()
+    for bb in range(B):
+        n = lens[bb]
+        ref = _ref_pair(x[bb : bb + 1, :n], w1, b1, w2, b2, k, dil, 0.1)
+        err = np.abs(out[bb, :n] - ref[0]).max()
+        assert err < 3e-4, (C, k, dil, bb, err)
+
+
+def test_fused_and_unfused_generator_agree(eng, hifigan_params):
+    mel = synthetic.mel_input(21, 2, 50)
+    nf = np.array([50, 31], np.int32)
+    eng.set_fused_pairs(True)
+    a = eng.mel2wave(mel, n_frames=nf)
+    eng.set_fused_pairs(False)
+    b = eng.mel2wave(mel, n_frames=nf)
+    eng.set_fused_pairs(True)
+    assert np.abs(a - b).max() < 1e-4

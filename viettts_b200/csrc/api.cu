@@ -275,6 +275,7 @@ int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16) {
   if (host_out_256x16) VTTS_CUDA(cudaMemcpy(host_out_256x16, ctx->d_tc_dbg, 256 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   VTTS_CUDA(cudaMemset(ctx->d_tc_dbg, 0, 256 * 16 * sizeof(long long)));
   ctx->tc_dbg_on = (enable & 1) != 0;
+  if (enable & 0x200) ctx->fuse_pairs = (enable >> 10) & 1;        // bit 9 set: bit 10 selects fused ResBlock pairs (tuning aid)
   if (enable & 0x100) ctx->tc_variant = (enable >> 4) & 0xF;   // bit 8 set: bits 4..7 select the tile-shape variant (tuning aid)
   return VTTS_OK;
 }
@@ -311,6 +312,28 @@ int vtts_debug_conv1d(vtts_ctx* ctx, int precision, const float* x_dev, const fl
     }
   }
   VTTS_CUDA(cudaDeviceSynchronize());
+  return VTTS_OK;
+}
+
+int vtts_debug_pair(vtts_ctx* ctx, const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev,
+                    const float* b2_dev, const int32_t* len_dev, int B, int T, int C, int k, int dil, float slope, float* out_dev) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  void* wpk = nullptr;
+  const size_t bytes = vtts_tc_packed_elems(k, C, C) * 2;
+  VTTS_CUDA(cudaMalloc(&wpk, 2 * bytes));
+  int rc = vtts_tc_pack_weights(ctx, w1_dev, wpk, k, C, C, 0, C);
+  if (!rc) rc = vtts_tc_pack_weights(ctx, w2_dev, (char*)wpk + bytes, k, C, C, 0, C);
+  if (rc) { cudaFree(wpk); return rc; }
+  TcPairLaunch PL;
+  memset(&PL, 0, sizeof(PL));
+  PL.nprob = 1; PL.N = C; PL.B = B; PL.T_rows = T; PL.len = len_dev; PL.len_mul = 1; PL.slope = slope;
+  PL.p[0] = TcPairProb{x_dev, wpk, (char*)wpk + bytes, b1_dev, b2_dev, out_dev, k, dil};
+  rc = vtts_launch_tc_pair(ctx, PL, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(wpk);
+  if (rc) return rc;
+  if (e != cudaSuccess) return ctx->fail(VTTS_ERR_CUDA, "debug_pair: %s", cudaGetErrorString(e));
   return VTTS_OK;
 }
 

@@ -287,6 +287,20 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
       const int d = vc::hg_dil(m);
       const float* src[3];
       for (int j = 0; j < 3; ++j) src[j] = (m == 0) ? hb.X : (m == 1 ? hb.A[par][j] : hb.Bb[j]);
+      if (tc && ctx->fuse_pairs && Co <= 64) {
+        // ---- fused pair: conv(d) -> lrelu -> conv(1) -> + x, intermediate kept on chip (tc_pair.cu) ----
+        TcPairLaunch PL;
+        memset(&PL, 0, sizeof(PL));
+        PL.nprob = 3; PL.N = Co; PL.B = B; PL.T_rows = rows; PL.len = n_frames; PL.len_mul = scale; PL.slope = 0.1f;
+        for (int j = 0; j < 3; ++j) {
+          const int kk = vc::hg_rbk(j), n = i * 3 + j;
+          PL.p[j] = TcPairProb{src[j], ctx->hg_wpk_t[n * 6 + m], ctx->hg_wpk_t[n * 6 + 3 + m], W[hgi::RB_B(n, 0, m)], W[hgi::RB_B(n, 1, m)],
+                               (m == 1) ? hb.Bb[j] : hb.A[par][j], kk, d};
+        }
+        rc = vtts_launch_tc_pair(ctx, PL, st);
+        if (rc) return rc;
+        continue;
+      }
       if (tc) {
         // ---- bf16x3 tensor-core path (tc_conv.cu) ----
         TcLaunch TL;

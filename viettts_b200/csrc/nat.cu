@@ -452,9 +452,11 @@ __device__ __forceinline__ float4 warp_reduce_rows(float (&acc)[RG][4], int lane
   return make_float4(a1[0], a1[1], a1[2], a1[3]);
 }
 
-// one LSTM layer for the staged rows: z partials -> part[warp][row][16] -> zs[row][16]
+// partial LSTM pre-activations for the staged rows: zout[row][16] = xs[row][0:64*SL] . w  (+ zadd[row][16])
+// (xs already points at the first column of the K segment; thread (ks, cg) owns rows ks*SL.. of the segment)
 template <int SL>
-__device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const float (&w)[SL][4], int ngroups, float* part, float* zs) {
+__device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const float (&w)[SL][4], int ngroups, float* part, float* zout,
+                                           const float* zadd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ks = tid >> 2;
   for (int g = 0; g < ngroups; ++g) {
@@ -481,10 +483,63 @@ __device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const f
   }
   __syncthreads();
   for (int o = tid; o < ngroups * RG * NCOL; o += SCAN_THREADS) {
-    float s = 0.f;
+    float s = zadd ? zadd[o] : 0.f;
 #pragma unroll
     for (int wv = 0; wv < SCAN_THREADS / 32; ++wv) s += part[(size_t)wv * DEC_XR * NCOL + o];
-    zs[o] = s;
+    zout[o] = s;
+  }
+  __syncthreads();
+}
+
+// same, accumulating two K segments (xa: 64*SLA columns with weights wa; xb: 64*SLB columns with wb) before ONE reduction
+template <int SLA, int SLB>
+__device__ __forceinline__ void dec_matmul2(const float* __restrict__ xa, const float (&wa)[SLA][4], const float* __restrict__ xb,
+                                            const float (&wb)[SLB][4], int ngroups, float* part, float* zout, const float* zadd) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ks = tid >> 2;
+  for (int g = 0; g < ngroups; ++g) {
+    float acc[RG][4];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    const float* xk = xa + (size_t)(g * RG) * DEC_KPAD + ks * SLA;
+#pragma unroll
+    for (int kk = 0; kk < SLA; kk += 4) {
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)r * DEC_KPAD + kk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[r][c] = fmaf(xv.x, wa[kk + 0][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.y, wa[kk + 1][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.z, wa[kk + 2][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.w, wa[kk + 3][c], acc[r][c]);
+        }
+      }
+    }
+    const float* xk2 = xb + (size_t)(g * RG) * DEC_KPAD + ks * SLB;
+#pragma unroll
+    for (int kk = 0; kk < SLB; kk += 4) {
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(xk2 + (size_t)r * DEC_KPAD + kk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[r][c] = fmaf(xv.x, wb[kk + 0][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.y, wb[kk + 1][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.z, wb[kk + 2][c], acc[r][c]);
+          acc[r][c] = fmaf(xv.w, wb[kk + 3][c], acc[r][c]);
+        }
+      }
+    }
+    const float4 s = warp_reduce_rows(acc, lane);
+    *reinterpret_cast<float4*>(part + ((size_t)warp * DEC_XR + g * RG + (lane >> 2)) * NCOL + (lane & 3) * 4) = s;
+  }
+  __syncthreads();
+  for (int o = tid; o < ngroups * RG * NCOL; o += SCAN_THREADS) {
+    float s = zadd ? zadd[o] : 0.f;
+#pragma unroll
+    for (int wv = 0; wv < SCAN_THREADS / 32; ++wv) s += part[(size_t)wv * DEC_XR * NCOL + o];
+    zout[o] = s;
   }
   __syncthreads();
 }
@@ -589,45 +644,54 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
     float* xs = sm;                                   // [DEC_XR][DEC_KPAD] = [p2 | h0 | h1]
     float* part = xs + DEC_XR * DEC_KPAD;             // [8][DEC_XR][16]
     float* zs = part + 8 * DEC_XR * NCOL;             // [DEC_XR][16]
-    float* cst = zs + DEC_XR * NCOL;                  // [2][DEC_XR][UPC]
+    float* zp0 = zs + DEC_XR * NCOL;                  // [DEC_XR][16] pre-accumulated h0_{t-1} . W0[h0 rows]
+    float* zp1 = zp0 + DEC_XR * NCOL;                 // [DEC_XR][16] pre-accumulated h1_{t-1} . W1[h1 rows] (+ p2 . W1[p2 rows])
+    float* cst = zp1 + DEC_XR * NCOL;                 // [2][DEC_XR][UPC]
     const int ks = tid >> 2, cgp = tid & 3;
-    float w0[SL0][4], w1[SL1][4];
+    constexpr int SLP = vc::PRENET / NSLICE, SLH = H / NSLICE;   // 4, 8
+    // register-resident weight slices, split by input segment so that each segment's product can be
+    // accumulated as soon as that segment is final
+    float w0p[SLP][4], w0h[SLH][4], w1p[SLP][4], w1h0[SLH][4], w1h1[SLH][4];
     {
-      const float* g0 = a.w0r + ((size_t)c * K0 + ks * SL0) * NCOL + cgp * 4;
+      auto ld = [&](float (&dst)[4], const float* base, int row) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * NCOL + cgp * 4));
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      };
+      const float* g0 = a.w0r + (size_t)c * K0 * NCOL;
+      const float* g1 = a.w1r + (size_t)c * K1 * NCOL;
 #pragma unroll
-      for (int i = 0; i < SL0; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(g0 + (size_t)i * NCOL));
-        w0[i][0] = v.x; w0[i][1] = v.y; w0[i][2] = v.z; w0[i][3] = v.w;
-      }
-      const float* g1 = a.w1r + ((size_t)c * K1 + ks * SL1) * NCOL + cgp * 4;
+      for (int i = 0; i < SLP; ++i) { ld(w0p[i], g0, ks * SLP + i); ld(w1p[i], g1, ks * SLP + i); }
 #pragma unroll
-      for (int i = 0; i < SL1; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(g1 + (size_t)i * NCOL));
-        w1[i][0] = v.x; w1[i][1] = v.y; w1[i][2] = v.z; w1[i][3] = v.w;
+      for (int i = 0; i < SLH; ++i) {
+        ld(w0h[i], g0, vc::PRENET + ks * SLH + i);
+        ld(w1h0[i], g1, vc::PRENET + ks * SLH + i);
+        ld(w1h1[i], g1, vc::PRENET + H + ks * SLH + i);
       }
     }
     for (int e = tid; e < 2 * DEC_XR * UPC; e += SCAN_THREADS) cst[e] = 0.f;
-    for (int e = tid; e < DEC_XR * DEC_KPAD; e += SCAN_THREADS) xs[e] = 0.f;   // rows >= B and the t=0 state are zero
+    for (int e = tid; e < 2 * DEC_XR * NCOL; e += SCAN_THREADS) zp0[e] = 0.f;   // zp0 and zp1 are adjacent
+    for (int e = tid; e < DEC_XR * DEC_KPAD; e += SCAN_THREADS) xs[e] = 0.f;    // rows >= B and the t=0 state are zero
     __syncthreads();
     const int ngroups = (B + RG - 1) / RG;
     for (int t = 0; t < N; ++t) {
       const int cur = t & 1, prv = cur ^ 1;
-      // ---- EA window: prefetch the state vectors that are already final: h0_{t-1}, h1_{t-1} ----
+      // ---- EA window (prenet CTAs are busy): products of the state that is already final ----
       if (t > 0) {
-        dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)prv * B * H, H, H, B);
+        // h0_{t-1} is still resident in xs (fetched as h0_t in phase D of the previous frame); only h1_{t-1} is new
         dec_fetch(xs, DEC_KPAD, vc::PRENET + H, a.h1 + (size_t)prv * B * H, H, H, B);
+        dec_matmul<SLH>(xs + vc::PRENET, w0h, ngroups, part, zp0, nullptr);     // its barriers also order the h1 fetch
+        dec_matmul<SLH>(xs + vc::PRENET + H, w1h1, ngroups, part, zp1, nullptr);
       }
       DEC_MARK(0)
       grid.sync();
       DEC_MARK(1)
-      // ---- B window: nothing to do ----
       DEC_MARK(2)
       grid.sync();
       DEC_MARK(3)
-      // ---- phase C: LSTM0 on [cond_t (hoisted), p2, h0_{t-1}] ----
+      // ---- phase C: LSTM0 = zc0[t] + p2 . W0[p2 rows] + (h0_{t-1} part) ----
       dec_fetch(xs, DEC_KPAD, 0, a.p2, vc::PRENET, vc::PRENET, B);
       __syncthreads();
-      dec_matmul<SL0>(xs, w0, ngroups, part, zs);
+      dec_matmul<SLP>(xs, w0p, ngroups, part, zs, zp0);
       if (tid < B * UPC) {
         const int r = tid / UPC, uu = tid % UPC;
         const float* zc = a.zc0 + ((size_t)r * N + t) * (4 * H) + c * UPC + uu;
@@ -639,10 +703,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       DEC_MARK(4)
       grid.sync();
       DEC_MARK(5)
-      // ---- phase D: LSTM1 on [cond_t (hoisted), p2, h0_t, h1_{t-1}] ----
+      // ---- phase D: LSTM1 = zc1[t] + p2 . W1[p2 rows] + h0_t . W1[h0 rows] + (h1_{t-1} part) ----
       dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)cur * B * H, H, H, B);
       __syncthreads();
-      dec_matmul<SL1>(xs, w1, ngroups, part, zs);
+      dec_matmul2<SLP, SLH>(xs, w1p, xs + vc::PRENET, w1h0, ngroups, part, zs, zp1);
       if (tid < B * UPC) {
         const int r = tid / UPC, uu = tid % UPC;
         const float* zc = a.zc1 + ((size_t)r * N + t) * (4 * H) + c * UPC + uu;
@@ -659,44 +723,50 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
   } else if (c < DEC_LSTM + DEC_PRE) {
     // =============================== prenet role ===============================
     const int q = c - DEC_LSTM;                        // columns 16q .. 16q+15 of p1 and p2
-    float* xs = sm;                                    // [32][PRE_KP]  (phase EA: [h0|h1]; phase B: p1 in the first 260 floats)
-    float* wcs = xs + 32 * PRE_KP;                     // [2][1024+64][8]
-    float* w2s = wcs + 2 * (2 * H + NSLICE) * 8;       // [2][256+64][8]
-    float* part = w2s + 2 * (vc::PRENET + NSLICE) * 8; // [8][32][8]
+    constexpr int XP = H + 4;                          // 516: row pitch of the 512-wide staging buffer
+    constexpr int WCB = (2 * H + 2 * H / 8) * 8;       // (Wo.W1) half-block: 1024 rows + one pad row per 8, x 8 columns
+    constexpr int W2B = (vc::PRENET + NSLICE) * 8;
+    float* xs = sm;                                    // [32][XP]: h1_{t-1} (EA), p1 (B), h0_t (D window)
+    float* wcs = xs + 32 * XP;                         // [2][WCB]
+    float* w2s = wcs + 2 * WCB;                        // [2][W2B]
+    float* part = w2s + 2 * W2B;                       // [8][32][8]
     float* outv = part + 8 * 256;                      // [256]
+    float* pp1 = outv + 256;                           // [2][256] h0 half of p1's pre-activation, computed one phase early
     for (int hf = 0; hf < 2; ++hf) {
-      pre_load_w8(wcs + (size_t)hf * (2 * H + NSLICE) * 8, a.wc + (size_t)q * 2 * H * 16, 2 * H, 16, 16, hf * 8);
-      pre_load_w8(w2s + (size_t)hf * (vc::PRENET + NSLICE) * 8, a.wp2 + (size_t)q * vc::PRENET * 16, vc::PRENET, 4, 16, hf * 8);
+      pre_load_w8(wcs + (size_t)hf * WCB, a.wc + (size_t)q * 2 * H * 16, 2 * H, 8, 16, hf * 8);
+      pre_load_w8(w2s + (size_t)hf * W2B, a.wp2 + (size_t)q * vc::PRENET * 16, vc::PRENET, 4, 16, hf * 8);
     }
-    for (int e = tid; e < 32 * PRE_KP; e += SCAN_THREADS) xs[e] = 0.f;
+    for (int e = tid; e < 32 * XP; e += SCAN_THREADS) xs[e] = 0.f;
+    for (int e = tid; e < 512; e += SCAN_THREADS) pp1[e] = 0.f;
     __syncthreads();
     const int orow = tid >> 3, ocol = tid & 7;         // output handled by this thread after a pre_gemm8 pass
+    constexpr int H1OFF = (H + H / 8) * 8;             // first padded row of the h1 half inside a WCB block
     for (int t = 0; t < N; ++t) {
-      const int prv = (t & 1) ^ 1;
-      // ---- phase EA: p1(t) ----
+      const int cur = t & 1, prv = cur ^ 1;
+      // ---- phase EA: p1(t) = drop(relu(pp1 + h1_{t-1} . Wc[512:1024] + bc)) ----
       if (t > 0) {
-        dec_fetch(xs, PRE_KP, 0, a.h0 + (size_t)prv * B * H, H, H, B);
-        dec_fetch(xs, PRE_KP, H, a.h1 + (size_t)prv * B * H, H, H, B);
+        dec_fetch(xs, XP, 0, a.h1 + (size_t)prv * B * H, H, H, B);
         __syncthreads();
         for (int hf = 0; hf < 2; ++hf) {
-          pre_gemm8<16>(xs, PRE_KP, wcs + (size_t)hf * (2 * H + NSLICE) * 8, part, outv);
+          pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB + H1OFF, part, outv);
           if (orow < B) {
             const int u = q * 16 + hf * 8 + ocol;
-            const float v = fmaxf(outv[tid] + __ldg(a.bc + u), 0.f);
+            const float v = fmaxf(outv[tid] + pp1[hf * 256 + tid] + __ldg(a.bc + u), 0.f);
             a.p1[(size_t)orow * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + orow, t, N, 0, u);
           }
         }
-      } else if (tid < 32 * 16) {
+      } else {
         for (int e = tid; e < B * 16; e += SCAN_THREADS) a.p1[(size_t)(e >> 4) * vc::PRENET + q * 16 + (e & 15)] = 0.f;  // prenet(0) = 0
       }
       DEC_MARK(0)
       grid.sync();
       DEC_MARK(1)
       // ---- phase B: p2(t) = drop(relu(p1 . W2)) ----
-      dec_fetch(xs, PRE_KP, 0, a.p1, vc::PRENET, vc::PRENET, B);
+      __syncthreads();
+      dec_fetch(xs, XP, 0, a.p1, vc::PRENET, vc::PRENET, B);
       __syncthreads();
       for (int hf = 0; hf < 2; ++hf) {
-        pre_gemm8<4>(xs, PRE_KP, w2s + (size_t)hf * (vc::PRENET + NSLICE) * 8, part, outv);
+        pre_gemm8<4>(xs, XP, w2s + (size_t)hf * W2B, part, outv);
         if (orow < B) {
           const int u = q * 16 + hf * 8 + ocol;
           const float v = fmaxf(outv[tid], 0.f);
@@ -708,6 +778,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       DEC_MARK(3)
       grid.sync();
       DEC_MARK(5)
+      // ---- D window: h0_t is final -> its half of p1(t+1)'s pre-activation ----
+      __syncthreads();
+      dec_fetch(xs, XP, 0, a.h0 + (size_t)cur * B * H, H, H, B);
+      __syncthreads();
+      for (int hf = 0; hf < 2; ++hf) {
+        pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB, part, outv);
+        pp1[hf * 256 + tid] = outv[tid];
+      }
+      __syncthreads();
+      DEC_MARK(6)
       grid.sync();
       DEC_MARK(7)
     }
@@ -774,8 +854,8 @@ constexpr size_t enc_scan_smem() {
   return ((size_t)(vc::ENC_D + NSLICE) * NCOL + RG * (vc::ENC_D + 4) + 8 * RG * NCOL + RG * NCOL + MAX_ROWS * UPC) * 4;
 }
 constexpr size_t dec_scan_smem() {
-  constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + DEC_XR * NCOL + 2 * DEC_XR * UPC;
-  constexpr size_t pre = (size_t)32 * PRE_KP + 2 * (2 * vc::DEC_H + NSLICE) * 8 + 2 * (vc::PRENET + NSLICE) * 8 + 8 * 256 + 256;
+  constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + 3 * DEC_XR * NCOL + 2 * DEC_XR * UPC;
+  constexpr size_t pre = (size_t)32 * (vc::DEC_H + 4) + 2 * (2 * vc::DEC_H + 2 * vc::DEC_H / 8) * 8 + 2 * (vc::PRENET + NSLICE) * 8 + 8 * 256 + 256 + 512;
   constexpr size_t proj = (size_t)32 * PRE_KP + 2 * (2 * vc::DEC_H + NSLICE) * 8 + 8 * 256 + 256;
   constexpr size_t m1 = lstm > pre ? lstm : pre;
   return (m1 > proj ? m1 : proj) * 4;

@@ -26,136 +26,35 @@
 
 #include <algorithm>
 
+#include "tc_common.cuh"
 #include "vtts_internal.cuh"
 
 namespace {
 
+using namespace tcx;
+
 constexpr int NA = 4;               // activation stages
-constexpr int NW = 4;               // weight stages
+constexpr int NW_MAX = 8;            // weight stages: 6 x 16 KB for N = 256, 8 smaller ones otherwise (covers the L2 latency)
 constexpr int NTHREADS = 448;     // 4 epilogue + MMA + weight producer + 8 converter warps
 constexpr int NCONV = 256;        // converter threads
 constexpr int NGRP = 2;           // independent converter groups (alternate chunks -> two chunks in flight)
 constexpr int GRP_THREADS = NCONV / NGRP;
-constexpr long long SPIN_TIMEOUT = 4000000000LL;  // ~2 s of SM clocks: trap instead of hanging the GPU
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __noinline__ void spin_fail(int* err, int code) {
-  if (err) atomicExch(err, code);
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > SPIN_TIMEOUT) spin_fail(err, code);
-  }
-}
-// wait and add the stalled cycles to a per-role counter (profiling aid, see vtts_debug_tc_stats)
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > SPIN_TIMEOUT) spin_fail(err, code);
-  }
-  acc += clock64() - t0;
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N
-__host__ __device__ constexpr uint32_t make_idesc(int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// one elected lane of a fully converged warp (elect.sync): lets ptxas issue uniform-datapath
-// instructions (UTCHMMA, UTCBAR) without a per-thread waterfall loop
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ float lrelu(float v, float s) { return v >= 0.f ? v : s * v; }
-
-// split 4 floats into packed bf16 hi / lo
-__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                      h3 = __float2bfloat16_rn(v.w);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                      l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
-}
 
 // MT  = M-tiles (128 rows) per super tile, NPH = output phases accumulated per tile (ConvTranspose), the
 // accumulator set of a tile is NPH*MT*N TMEM columns; two sets (epilogue overlaps the next tile's MMAs) when
 // they fit in the 512 columns.
-template <int N, int MT_, int NPH_>
+template <int N, int MT_, int NPH_, int STK_ = 0>
 struct TcCfg {
   static constexpr int MT = MT_;
   static constexpr int NPH = NPH_;
+  static constexpr int STK = STK_;            // 1: A_hi x [W_hi | W_lo] as ONE MMA of width 2N (main | aux accumulator columns)
+  static constexpr int DW = STK ? 2 * N : N;  // accumulator columns per (phase, M tile)
+  static constexpr int NW = N == 256 ? 6 : ((N == 128 && MT_ == 4) ? 4 : NW_MAX);
   static constexpr int R = 128 * MT;          // output rows per super tile
   static constexpr int RA = R + 64;           // allocated activation rows per stage (halo <= 50)
   static constexpr int A_STAGE = RA * 64;     // bytes: 2 planes x 2 k-halves x RA rows x 16 B
   static constexpr int W_STAGE = N * 64;      // bytes: 2 planes x 2 k-halves x N rows x 16 B
-  static constexpr int ACC_COLS = NPH * MT * N;
+  static constexpr int ACC_COLS = NPH * MT * DW;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_RAW = NACC * ACC_COLS;
@@ -168,10 +67,10 @@ struct TcCfg {
 
 // EPI = 0: bias (+ residual) only -- the HiFiGAN generator's hot path.  EPI = 1: bias, eval BatchNorm,
 // tanh / relu, residual, partial N tile (acoustic model convs and GEMMs).
-template <int N, int EPI, int MT_, int NPH_>
+template <int N, int EPI, int MT_, int NPH_, int STK_>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_constant__ TcLaunch L) {
-  using Cfg = TcCfg<N, MT_, NPH_>;
-  constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA, NPH = Cfg::NPH;
+  using Cfg = TcCfg<N, MT_, NPH_, STK_>;
+  constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA, NPH = Cfg::NPH, STK = Cfg::STK, DW = Cfg::DW, NW = Cfg::NW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_st = smem;
@@ -246,7 +145,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       const uint32_t a_st_u32 = smem_u32(a_st), w_st_u32 = smem_u32(w_st);
       // descriptor templates: start address added per use (row stride 16 B == 1 descriptor address unit)
       const uint64_t a_tmpl = make_desc(0, RA * 16, 128);
-      const uint64_t b_tmpl = make_desc(0, N * 16, 128);
+      const uint64_t b_tmpl = make_desc(0, 2 * N * 16, 128);     // k-half blocks are 2N rows apart ([hi rows | lo rows])
+      constexpr uint32_t idesc2 = make_idesc(2 * N <= 256 ? 2 * N : N);
       TILE_LOOP_BEGIN
         (void)b; (void)tau0;
         const int k = P.k, dil = P.dil;
@@ -265,7 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
               tc_fence_after();
               const uint32_t w_base16 = (w_st_u32 + sw * Cfg::W_STAGE) >> 4;
               const uint64_t b_hi = b_tmpl | (uint64_t)w_base16;
-              const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + 2 * N);
+              const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + N);
               const uint32_t first = (c | j) != 0 ? 1u : 0u;
               if (elect_one()) {
 #pragma unroll
@@ -273,10 +173,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
                   const uint32_t row = a_base16 + mt * 128 + shift + j * dil;
                   const uint64_t a_hi = a_tmpl | (uint64_t)row;
                   const uint64_t a_lo = a_tmpl | (uint64_t)(row + 2 * RA);
-                  const uint32_t d = d0 + (ph * MT + mt) * N;
-                  umma(d, a_hi, b_hi, idesc, first);
-                  umma(d, a_hi, b_lo, idesc, 1u);
-                  umma(d, a_lo, b_hi, idesc, 1u);
+                  const uint32_t d = d0 + (ph * MT + mt) * DW;
+                  if constexpr (STK) {
+                    umma(d, a_hi, b_hi, idesc2, first);     // [main | aux] (+)= A_hi . [W_hi | W_lo]
+                    umma(d, a_lo, b_hi, idesc, 1u);         // main += A_lo . W_hi
+                  } else {
+                    umma(d, a_hi, b_hi, idesc, first);
+                    umma(d, a_hi, b_lo, idesc, 1u);
+                    umma(d, a_lo, b_hi, idesc, 1u);
+                  }
                 }
                 umma_commit(&w_empty[sw]);
               }
@@ -429,8 +334,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
         const int pm = it / NCHUNK, c0 = (it - pm * NCHUNK) * 32;
         const int mt = pm % MT, ooff = P.out_off_ph[pm / MT];
         uint32_t r[32];
-        tmem_ld16(taddr0 + pm * N + c0, r);
-        tmem_ld16(taddr0 + pm * N + c0 + 16, r + 16);
+        tmem_ld16(taddr0 + pm * DW + c0, r);
+        tmem_ld16(taddr0 + pm * DW + c0 + 16, r + 16);
+        uint32_t r2[STK ? 32 : 1];
+        if constexpr (STK) {
+          tmem_ld16(taddr0 + pm * DW + N + c0, r2);
+          tmem_ld16(taddr0 + pm * DW + N + c0 + 16, r2 + 16);
+        }
         float4 rs_next[8];
         if (it + 1 < NPH * MT * NCHUNK) load_resid(it + 1, rs_next);
         const bool col_ok = !EPI || (c0 + tch * 4 < n_valid);
@@ -444,6 +354,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
           }
         }
         tmem_ld_wait();
+        if constexpr (STK) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(r2[q]));
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(slab + lane * Cfg::EPI_PITCH + q * 16) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
@@ -490,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
 }
 
 // fp32 Haiku conv weight w[k][Cin][Cout_total] -> packed bf16 blocks for output columns [n0, n0+N):
-//   [chunk c = Cin/16][tap j][plane hi|lo][k-half][n][8]
+//   [chunk c = Cin/16][tap j][k-half][plane hi|lo][n][8]
 __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int k, int Cin, int Cout_total, int n0, int N) {
   const size_t total = (size_t)k * Cin * N;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -502,17 +416,17 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const int c = i / 16, kh = (i % 16) / 8, e = i % 8;
     const size_t blk = ((size_t)c * k + j) * (size_t)(4 * N * 8);
-    dst[blk + ((size_t)(0 * 2 + kh) * N + n) * 8 + e] = hi;
-    dst[blk + ((size_t)(1 * 2 + kh) * N + n) * 8 + e] = lo;
+    dst[blk + ((size_t)(kh * 2 + 0) * N + n) * 8 + e] = hi;   // [k-half][plane hi|lo][n][8]: hi and lo rows of a k-half are
+    dst[blk + ((size_t)(kh * 2 + 1) * N + n) * 8 + e] = lo;   // adjacent, so [W_hi | W_lo] is also one 2N-row operand
   }
 }
 
-template <int N, int EPI, int MT, int NPH>
+template <int N, int EPI, int MT, int NPH, int STK = 0>
 int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
-  using Cfg = TcCfg<N, MT, NPH>;
+  using Cfg = TcCfg<N, MT, NPH, STK>;
   static bool attr_done = false;
   if (!attr_done) {
-    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, MT, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, MT, NPH, STK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   for (int i = 0; i < L.nprob; ++i) {
@@ -528,7 +442,7 @@ int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   L.tiles_per_row = (L.T_rows + Cfg::R - 1) / Cfg::R;
   L.ntiles = L.nprob * L.tiles_per_row * L.B;
   const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
-  tc_conv_kernel<N, EPI, MT, NPH><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  tc_conv_kernel<N, EPI, MT, NPH, STK><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
   ctx->launches++;
   VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
@@ -541,7 +455,7 @@ int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   const int nph = L.nphase > 1 ? L.nphase : 1;
   if constexpr (N == 256) {
     if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=256 supports single-phase tiles only");
-    if (ctx->tc_variant == 0) return launch_cfg<256, EPI, 2, 1>(ctx, L, st);
+    if (ctx->tc_variant == 0) return launch_cfg<256, EPI, 2, 1>(ctx, L, st);   // single accumulator set (slower, kept for A/B runs)
     return launch_cfg<256, EPI, 1, 1>(ctx, L, st);
   } else if constexpr (N == 128) {
     if (nph == 4) return launch_cfg<128, EPI, 1, 4>(ctx, L, st);
@@ -551,10 +465,12 @@ int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   } else if constexpr (N == 64) {
     if (nph == 2) return launch_cfg<64, EPI, 2, 2>(ctx, L, st);
     if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=64 supports 1 or 2 phases");
+    if (ctx->tc_variant == 2) return launch_cfg<64, EPI, 2, 1, 1>(ctx, L, st);   // experimental: stacked [W_hi|W_lo] (measured slower: 298 vs 355 TFLOP/s)
     return launch_cfg<64, EPI, 4, 1>(ctx, L, st);
   } else {
     if (nph == 2) return launch_cfg<32, EPI, 4, 2>(ctx, L, st);
     if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=32 supports 1 or 2 phases");
+    if (ctx->tc_variant == 2) return launch_cfg<32, EPI, 4, 1, 1>(ctx, L, st);   // experimental: stacked [W_hi|W_lo] (no gain measured)
     return launch_cfg<32, EPI, 4, 1>(ctx, L, st);
   }
 }

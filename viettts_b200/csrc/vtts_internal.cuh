@@ -107,12 +107,37 @@ struct TcLaunch {
   long long* dbg;             // optional [grid][16] per-role stall counters (vtts_debug_tc_stats)
 };
 
+// ---- fused ResBlock pair (tc_pair.cu): out = conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x, C = N channels ----
+struct TcPairProb {
+  const float* x;        // [B][T_rows][N] input and residual
+  const void* w1pk;      // packed bf16 hi/lo weights of the dilated conv (vtts_tc_pack_weights)
+  const void* w2pk;      // ... of the dilation-1 conv
+  const float* b1;
+  const float* b2;
+  float* out;            // [B][T_rows][N], must differ from x
+  int k, dil;
+};
+
+struct TcPairLaunch {
+  TcPairProb p[3];
+  int nprob;
+  int N;
+  int B, T_rows;
+  const int* len;
+  int len_mul;
+  float slope;
+  int tile_start[3], tiles_per_row[3], ntiles;   // filled by the launcher
+  int* err;
+  long long* dbg;
+};
+
 struct vtts_ctx {
   int device = 0;
   int precision = 1;            // 0 = strict fp32 (FMA pipe), 1 = bf16x3 on tcgen05 tensor cores (default)
   int* d_err = nullptr;
   long long* d_tc_dbg = nullptr;   // [256][16] profiling counters of the last tensor-core conv launch
   bool tc_dbg_on = false;
+  int fuse_pairs = 0;              // 1 = ResBlock pairs with C <= 64 run in the fused tc_pair kernel (cuts HBM traffic 2.5x but is MMA-issue bound: off by default)
   int tc_variant = 1;              // tile-shape variant of the tensor-core conv (see TcCfg); 1 = double-buffered accumulators for N >= 128
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
@@ -195,6 +220,8 @@ int vtts_launch_conv(vtts_ctx* ctx, const ConvLaunch& L, cudaStream_t st);
 size_t vtts_tc_packed_elems(int k, int Cin, int N);
 int vtts_tc_pack_weights(vtts_ctx* ctx, const float* w, void* dst, int k, int Cin, int Cout_total, int n0, int N);
 int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st);
+// tc_pair.cu
+int vtts_launch_tc_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);
 // generic dispatch: runs `L` on the tensor-core path when ctx->precision == 1 and packed weights are given
 // (wpk[prob * ntile + tile], ntile = ceil(Cout/256) tiles of width vtts_tc_tile_n(Cout)), else on the FP32 path
 int vtts_tc_tile_n(int Cout);

@@ -92,6 +92,19 @@ class Engine:
                                             B, T, Cin, Cout, int(k), int(dil), float(pre_slope), _ptr(out)))
         return out
 
+    def debug_pair(self, x_t, w1_t, b1_t, w2_t, b2_t, k, dil, slope=0.1, len_t=None):
+        """Test hook: one fused ResBlock pair on torch CUDA tensors (tensor-core path)."""
+        import torch
+        B, T, Cc = x_t.shape
+        out = torch.empty_like(x_t)
+        self._ck(self.lib.vtts_debug_pair(self.h, _ptr(x_t), _ptr(w1_t), _ptr(b1_t), _ptr(w2_t), _ptr(b2_t), _ptr(len_t),
+                                          B, T, Cc, int(k), int(dil), float(slope), _ptr(out)))
+        return out
+
+    def set_fused_pairs(self, on: bool):
+        """Run the C <= 64 ResBlock pairs in the fused tc_pair kernel (default: two tensor-core conv launches)."""
+        self._ck(self.lib.vtts_debug_tc_stats(self.h, 0x200 | ((1 if on else 0) << 10), None))
+
     def tc_stats(self, enable=True, variant=None):
         """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats);
         `variant` (0/1) optionally selects the tile-shape variant for later launches."""
