@@ -313,6 +313,31 @@ def run_ours(args):
     h2d = tokens.nbytes + durs.nbytes + nfs.nbytes
     d2h = wav_h.nbytes
 
+    # ---- STFT/log-mel kernel (MelFilter, nat/dsp.py:104-128): HBM-bound streaming kernel, measured separately ----
+    mel_info = None
+    if rank == 0:
+        S = 79872
+        MB = 512                                     # 512 x 5 s = 164 MB of samples: larger than L2
+        wav_m = torch.rand((MB, S), dtype=torch.float32, device=dev) - 0.5
+        mel_m = torch.empty((MB, S // C.HOP, C.MEL_DIM), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            eng.melspec_forward(wav_m, out=mel_m)
+        m0, m1 = ev(), ev()
+        m0.record()
+        for _ in range(5):
+            eng.melspec_forward(wav_m, out=mel_m)
+        m1.record()
+        torch.cuda.synchronize()
+        mms = m0.elapsed_time(m1) / 5
+        mbytes = MB * S * 5.25                      # 4 B in + 1.25 B out per sample
+        pkm = peaks()
+        mflop = MB * (S // C.HOP) * 29704.0         # sparse-filterbank FLOP count per frame
+        mel_info = dict(samples_per_s=MB * S / (mms / 1e3), ms=mms, achieved_gbs=mbytes / (mms / 1e3) / 1e9,
+                        peak_gbs=pkm["hbm_gbs"], frac_hbm=mbytes / (mms / 1e3) / 1e9 / pkm["hbm_gbs"],
+                        achieved_tflops_fp32=mflop / (mms / 1e3) / 1e12, batch=MB, samples_per_row=S,
+                        note="FFT-1024 in shared memory (5 radix-4 passes, 2 frames per complex FFT); latency/compute bound, not yet at the HBM roofline")
+        del wav_m, mel_m
+
     if rank == 0:
         pk = peaks()
         frames = int(nfs.sum())
@@ -350,7 +375,7 @@ def run_ours(args):
                           peak_source=pk["source"] + ", sustained bf16 dense",
                           note=("algorithmic fp32 FLOPs; the bf16x3 path issues 3 bf16 MMAs per algorithmic product, so 1/3 of the bf16 peak is its ceiling"
                                 if args.precision != "fp32" else "strict-fp32 path runs on the FP32 FMA pipe (nominal 74 TFLOP/s)")),
-            clocks=clocks, weights=dict(bytes=wbytes, broadcast_s=t_w),
+            clocks=clocks, weights=dict(bytes=wbytes, broadcast_s=t_w), melspec=mel_info,
         )
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(synthetic.hifigan_params(1234), synthetic.acoustic_ckpt(1234), args.phonemes, args.seconds)

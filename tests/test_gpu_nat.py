@@ -152,3 +152,23 @@ def test_synthesize_equals_two_stage(eng, acoustic_ckpt, hifigan_params):
     mel2 = eng.predict_mel(tk[None], d[None], n_frames=[n], masks=masks)
     assert np.array_equal(mel, mel2)
     assert np.array_equal(wav, eng.mel2wave(mel2))
+
+
+def test_mixed_length_bucketed_synthesis(eng, hifigan_params):
+    """configs[4]-style mixed lengths: bucketed ragged batches must return, per utterance, what a
+    single-utterance call returns (dropout off so that rows do not depend on their batch position)."""
+    eng.load_hifigan(hifigan_params)
+    rng = np.random.default_rng(3)
+    utts = []
+    for i in range(10):
+        L = int(rng.integers(8, 40))
+        tk, d, n = _utt(200 + i, L, None)
+        utts.append((tk, d))
+    wavs = eng.synthesize_many(utts, max_rows=4)
+    assert len(wavs) == len(utts)
+    for i in (0, 3, 7, 9):
+        tk, d = utts[i]
+        n = int(np.sum(d, dtype=np.float32))
+        alone = eng.synthesize(tk[None], d[None], n_frames=[n])
+        assert wavs[i].shape == (n * 256,)
+        assert np.abs(wavs[i] - alone[0]).max() < 1e-5

@@ -213,6 +213,33 @@ class Engine:
                 mel[sl] = m
         return (wav, mel) if return_mel else wav
 
+    def synthesize_many(self, utterances, seed=None, masks=None, max_pad_frac=0.08, max_rows=32):
+        """Mixed-length workload (BASELINE configs[4]): `utterances` is a list of (tokens list[int],
+        durations_in_frames f32[L]).  They are bucketed by frame count so that padding stays below
+        `max_pad_frac`, each bucket runs as one ragged batch, and the waveforms come back in input order
+        (list of np.float32 [256*n_frames_i]).  Row i of any bucket equals utterance i run alone."""
+        from .parallel import bucket_by_length
+        nfs = [int(np.sum(np.asarray(d, np.float32), dtype=np.float32)) for _, d in utterances]
+        out = [None] * len(utterances)
+        for bucket in bucket_by_length(nfs, max_pad_frac, max_rows):
+            Lmax = max(len(utterances[i][0]) for i in bucket)
+            tok = np.zeros((len(bucket), Lmax), np.int32)
+            dur = np.zeros((len(bucket), Lmax), np.float32)
+            lens = np.zeros(len(bucket), np.int32)
+            for r, i in enumerate(bucket):
+                t, d = utterances[i]
+                tok[r, : len(t)] = t
+                dur[r, : len(t)] = d
+                lens[r] = len(t)
+            nf = np.asarray([nfs[i] for i in bucket], np.int32)
+            m = None if masks is None else np.stack([np.asarray(masks[i])[: nf.max()] if np.asarray(masks[i]).shape[0] >= nf.max()
+                                                     else np.pad(np.asarray(masks[i]), ((0, nf.max() - np.asarray(masks[i]).shape[0]), (0, 0), (0, 0)))
+                                                     for i in bucket])
+            wav = self.synthesize(tok, dur, lengths=lens, n_frames=nf, masks=m, seed=seed)
+            for r, i in enumerate(bucket):
+                out[i] = wav[r, : nfs[i] * config.HOP].copy()
+        return out
+
     def melspec(self, wav) -> np.ndarray:
         """MelFilter.__call__ (nat/dsp.py:115-128): wav f32 [B,S] -> log-mel [B,S/256,80]."""
         if not self._mel_loaded:
