@@ -101,11 +101,6 @@ __global__ void repack_proj_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
-__global__ void fill_kernel(int32_t* p, int v, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
-
 // ---- Gaussian upsampling (model.py:102-111) --------------------------------------------------------
 // out[b,n,:] = sum_l softmax_l(-(mid_l - n)^2/10) enc[b,l,:],  mid = cumsum(dur) - dur/2
 constexpr int UP_F = 8;  // frames per CTA
@@ -191,95 +186,6 @@ struct Seg {
   int stride;
 };
 
-// Copy resident weights [K][16] from global (this CTA's slice) into shared memory with one pad row
-// per K slice (slice length SL = K/64): physical row = k + k/SL, so that the two slices read in the
-// same quarter-warp phase land in different bank halves.
-__device__ void load_w16(float* wsm, const float* __restrict__ g, int K) {
-  const int SL = K / NSLICE;
-  for (int e = threadIdx.x; e < K * 4; e += SCAN_THREADS) {
-    int k = e >> 2, q = (e & 3) * 4;
-    float4 v = __ldg(reinterpret_cast<const float4*>(g + (size_t)k * NCOL + q));
-    *reinterpret_cast<float4*>(wsm + (size_t)(k + k / SL) * NCOL + q) = v;
-  }
-}
-
-// Stage `nr` (<= RG) batch rows of the concatenated input vector into xs[r][Kpad].
-// zero_row[r] != 0 zeroes the LAST segment of that row (ResetCore on the recurrent state).
-__device__ void stage_rows(float* xs, int Kpad, const Seg* segs, int nseg, int row0, int nr, const int* zero_last) {
-  int koff = 0;
-  for (int s = 0; s < nseg; ++s) {
-    const int n4 = segs[s].n >> 2;
-    for (int e = threadIdx.x; e < nr * n4; e += SCAN_THREADS) {
-      int r = e / n4, i4 = (e - r * n4) * 4;
-      float4 v = make_float4(0, 0, 0, 0);
-      const bool z = segs[s].p == nullptr || (zero_last && s == nseg - 1 && zero_last[r]);
-      if (!z) v = __ldcg(reinterpret_cast<const float4*>(segs[s].p + (size_t)(row0 + r) * segs[s].stride + i4));
-      *reinterpret_cast<float4*>(xs + (size_t)r * Kpad + koff + i4) = v;
-    }
-    koff += segs[s].n;
-  }
-  for (int e = threadIdx.x; e < (RG - nr) * (koff >> 2); e += SCAN_THREADS) {
-    int r = nr + e / (koff >> 2), i4 = (e % (koff >> 2)) * 4;
-    *reinterpret_cast<float4*>(xs + (size_t)r * Kpad + i4) = make_float4(0, 0, 0, 0);
-  }
-}
-
-// z[r][col] (RG x 16) = xs[r][0:K] . wsm[0:K][col]; result written to zs[r*16 + col].
-// Thread (ks = tid/4, cgp = tid%4) reduces K slice ks for 4 columns x 8 rows.
-__device__ void matmul16(const float* __restrict__ xs, int Kpad, const float* __restrict__ wsm, int K, float* part, float* zs) {
-  const int tid = threadIdx.x;
-  const int cgp = tid & 3, ks = tid >> 2;
-  const int SL = K / NSLICE;
-  float acc[RG][4];
-#pragma unroll
-  for (int r = 0; r < RG; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-  const float* xk = xs + ks * SL;
-  const float* wk = wsm + (size_t)(ks * SL + ks) * NCOL + cgp * 4;
-  for (int kk = 0; kk < SL; kk += 4) {
-    float4 xv[RG];
-#pragma unroll
-    for (int r = 0; r < RG; ++r) xv[r] = *reinterpret_cast<const float4*>(xk + (size_t)r * Kpad + kk);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float4 wv = *reinterpret_cast<const float4*>(wk + (size_t)(kk + e) * NCOL);
-#pragma unroll
-      for (int r = 0; r < RG; ++r) {
-        const float x = e == 0 ? xv[r].x : (e == 1 ? xv[r].y : (e == 2 ? xv[r].z : xv[r].w));
-        acc[r][0] = fmaf(x, wv.x, acc[r][0]);
-        acc[r][1] = fmaf(x, wv.y, acc[r][1]);
-        acc[r][2] = fmaf(x, wv.z, acc[r][2]);
-        acc[r][3] = fmaf(x, wv.w, acc[r][3]);
-      }
-    }
-  }
-  // reduce the 8 slices held by one warp (lane bits 2..4), then across the 8 warps through smem
-#pragma unroll
-  for (int r = 0; r < RG; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v = acc[r][c];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      acc[r][c] = v;
-    }
-  const int warp = tid >> 5, lane = tid & 31;
-  if (lane < 4) {
-#pragma unroll
-    for (int r = 0; r < RG; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) part[warp * (RG * NCOL) + r * NCOL + lane * 4 + c] = acc[r][c];
-  }
-  __syncthreads();
-  if (tid < RG * NCOL) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) s += part[w * (RG * NCOL) + tid];
-    zs[tid] = s;
-  }
-  __syncthreads();
-}
-
 // LSTM cell update for (row r, unit uu) from zs (hk.LSTM: i,g,f,o; forget bias +1)
 __device__ __forceinline__ float lstm_cell(const float* zs, int r, int uu, float zadd_i, float zadd_g, float zadd_f, float zadd_o, float& c) {
   const float zi = zs[r * NCOL + 0 * UPC + uu] + zadd_i;
@@ -299,57 +205,6 @@ struct EncScanArgs {
   float* out;             // [B][L][512]  (fwd | bwd)
   int B, L;
 };
-
-__global__ void __launch_bounds__(SCAN_THREADS, 1) enc_scan_kernel(const EncScanArgs a) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ __align__(16) float sm[];
-  constexpr int K = vc::ENC_D, H = vc::ENC_D, Kpad = K + 4;
-  float* wsm = sm;                               // [(K+64)][16]
-  float* xs = wsm + (K + NSLICE) * NCOL;         // [RG][Kpad]
-  float* part = xs + RG * Kpad;                  // [8][RG*16]
-  float* zs = part + 8 * RG * NCOL;              // [RG*16]
-  float* cst = zs + RG * NCOL;                   // [MAX_ROWS][UPC]
-  __shared__ int zero_row[RG];
-  const int dir = blockIdx.x / 64, c = blockIdx.x % 64, tid = threadIdx.x;
-  const int B = a.B, L = a.L;
-  load_w16(wsm, a.whr + ((size_t)dir * 64 + c) * K * NCOL, K);
-  for (int e = tid; e < MAX_ROWS * UPC; e += SCAN_THREADS) cst[e] = 0.f;
-  __syncthreads();
-  for (int s = 0; s < L; ++s) {
-    const int t = dir == 0 ? s : L - 1 - s;
-    const int tprev = dir == 0 ? t - 1 : t + 1;
-    for (int row0 = 0; row0 < B; row0 += RG) {
-      const int nr = min(RG, B - row0);
-      if (tid < RG) {
-        int z = 0;
-        if (tid < nr) {
-          const int len = a.lengths ? min(a.lengths[row0 + tid], L) : L;
-          // fwd: zero state at t=0.  bwd: ResetCore mask = (t >= len-1) (model.py:37,40)
-          z = dir == 0 ? (s == 0) : (s == 0 || t >= len - 1);
-        }
-        zero_row[tid] = z;
-      }
-      __syncthreads();
-      Seg seg;
-      seg.p = (s == 0) ? nullptr : a.out + (size_t)tprev * vc::ENC_OUT + dir * H;
-      seg.n = H;
-      seg.stride = L * vc::ENC_OUT;
-      stage_rows(xs, Kpad, &seg, 1, row0, nr, zero_row);
-      __syncthreads();
-      matmul16(xs, Kpad, wsm, K, part, zs);
-      if (tid < nr * UPC) {
-        const int r = tid / UPC, uu = tid % UPC, b = row0 + r;
-        const float* zx = a.zx + (((size_t)dir * B + b) * L + t) * (4 * H) + c * UPC + uu;
-        float cc = zero_row[r] ? 0.f : cst[b * UPC + uu];
-        const float h = lstm_cell(zs, r, uu, __ldg(zx), __ldg(zx + H), __ldg(zx + 2 * H), __ldg(zx + 3 * H), cc);
-        cst[b * UPC + uu] = cc;
-        a.out[((size_t)b * L + t) * vc::ENC_OUT + dir * H + c * UPC + uu] = h;
-      }
-      __syncthreads();
-    }
-    grid.sync();
-  }
-}
 
 // ---- autoregressive decoder scan (model.py:129-142) ------------------------------------------------
 // One cooperative grid of 148 CTAs, up to 32 batch rows per launch.
@@ -390,7 +245,7 @@ struct DecScanArgs {
 constexpr int DEC_XR = 32;                 // batch rows per launch
 constexpr int DEC_KPAD = vc::PRENET + 2 * vc::DEC_H + 4;   // 1284: [p2 | h0 | h1] + pad
 constexpr int DEC_CTAS = 148;
-constexpr int DEC_LSTM = 128, DEC_PRE = 16, DEC_PROJ = 4;
+constexpr int DEC_LSTM = 128, DEC_PRE = 16;   // + 4 projection CTAs = DEC_CTAS
 constexpr int PRE_KP = 2 * vc::DEC_H + 4;  // 1028: row pitch of the prenet CTAs' [h0 | h1] buffer
 
 // copy rows [0,nr) x [n floats] of a global matrix (row stride `stride`) into smem (row pitch `pitch`, column
@@ -454,7 +309,7 @@ __device__ __forceinline__ float4 warp_reduce_rows(float (&acc)[RG][4], int lane
 
 // partial LSTM pre-activations for the staged rows: zout[row][16] = xs[row][0:64*SL] . w  (+ zadd[row][16])
 // (xs already points at the first column of the K segment; thread (ks, cg) owns rows ks*SL.. of the segment)
-template <int SL>
+template <int SL, int PITCH = DEC_KPAD>
 __device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const float (&w)[SL][4], int ngroups, float* part, float* zout,
                                            const float* zadd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -463,12 +318,12 @@ __device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const f
     float acc[RG][4];
 #pragma unroll
     for (int r = 0; r < RG; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-    const float* xk = xs + (size_t)(g * RG) * DEC_KPAD + ks * SL;
+    const float* xk = xs + (size_t)(g * RG) * PITCH + ks * SL;
 #pragma unroll
     for (int kk = 0; kk < SL; kk += 4) {
 #pragma unroll
       for (int r = 0; r < RG; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)r * DEC_KPAD + kk);
+        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)r * PITCH + kk);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           acc[r][c] = fmaf(xv.x, w[kk + 0][c], acc[r][c]);
@@ -489,6 +344,71 @@ __device__ __forceinline__ void dec_matmul(const float* __restrict__ xs, const f
     zout[o] = s;
   }
   __syncthreads();
+}
+
+// ---- encoder BiLSTM scan (model.py:36-46) ---------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS, 1) enc_scan_kernel(const EncScanArgs a) {
+  // 128 CTAs: direction = cta / 64; CTA owns 4 hidden units (16 gate columns); its 256x16 slice of the recurrent
+  // matrix lives in registers (4 rows x 4 columns per thread); h_{t-1} of up to 32 rows is staged per step.
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float sm[];
+  constexpr int K = vc::ENC_D, H = vc::ENC_D, XP = K + 4, SL = K / NSLICE;   // 256, 256, 260, 4
+  float* xs = sm;                                // [32][XP]
+  float* part = xs + 32 * XP;                    // [8][32][16]
+  float* zs = part + 8 * DEC_XR * NCOL;          // [32][16]
+  float* cst = zs + DEC_XR * NCOL;               // [MAX_ROWS][UPC]
+  __shared__ int zero_row[DEC_XR];
+  const int dir = blockIdx.x / 64, c = blockIdx.x % 64, tid = threadIdx.x;
+  const int ks = tid >> 2, cgp = tid & 3;
+  const int B = a.B, L = a.L;
+  float wh[SL][4];
+  {
+    const float* g = a.whr + (((size_t)dir * 64 + c) * K + ks * SL) * NCOL + cgp * 4;
+#pragma unroll
+    for (int i = 0; i < SL; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g + (size_t)i * NCOL));
+      wh[i][0] = v.x; wh[i][1] = v.y; wh[i][2] = v.z; wh[i][3] = v.w;
+    }
+  }
+  for (int e = tid; e < MAX_ROWS * UPC; e += SCAN_THREADS) cst[e] = 0.f;
+  for (int e = tid; e < 32 * XP; e += SCAN_THREADS) xs[e] = 0.f;
+  __syncthreads();
+  for (int s = 0; s < L; ++s) {
+    const int t = dir == 0 ? s : L - 1 - s;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    for (int row0 = 0; row0 < B; row0 += DEC_XR) {
+      const int nr = min(DEC_XR, B - row0);
+      if (tid < DEC_XR) {
+        int z = 1;
+        if (tid < nr) {
+          const int len = a.lengths ? min(a.lengths[row0 + tid], L) : L;
+          // fwd: zero state at t=0.  bwd: ResetCore mask = (t >= len-1) (model.py:37,40)
+          z = dir == 0 ? (s == 0) : (s == 0 || t >= len - 1);
+        }
+        zero_row[tid] = z;
+      }
+      __syncthreads();
+      // stage h_{t-1} (zero for reset rows)
+      for (int e = tid; e < nr * (H / 4); e += SCAN_THREADS) {
+        const int r = e / (H / 4), i4 = (e - r * (H / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!zero_row[r]) v = __ldcg(reinterpret_cast<const float4*>(a.out + ((size_t)(row0 + r) * L + tprev) * vc::ENC_OUT + dir * H + i4));
+        *reinterpret_cast<float4*>(xs + (size_t)r * XP + i4) = v;
+      }
+      __syncthreads();
+      dec_matmul<SL, XP>(xs, wh, (nr + RG - 1) / RG, part, zs, nullptr);
+      if (tid < nr * UPC) {
+        const int r = tid / UPC, uu = tid % UPC, b = row0 + r;
+        const float* zx = a.zx + (((size_t)dir * B + b) * L + t) * (4 * H) + c * UPC + uu;
+        float cc = zero_row[r] ? 0.f : cst[b * UPC + uu];
+        const float h = lstm_cell(zs, r, uu, __ldg(zx), __ldg(zx + H), __ldg(zx + 2 * H), __ldg(zx + 3 * H), cc);
+        cst[b * UPC + uu] = cc;
+        a.out[((size_t)b * L + t) * vc::ENC_OUT + dir * H + c * UPC + uu] = h;
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  }
 }
 
 // same, accumulating two K segments (xa: 64*SLA columns with weights wa; xb: 64*SLB columns with wb) before ONE reduction
@@ -632,7 +552,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float sm[];
   constexpr int H = vc::DEC_H, K0 = vc::PRENET + H, K1 = vc::PRENET + 2 * H;
-  constexpr int SL0 = K0 / NSLICE, SL1 = K1 / NSLICE;   // 12, 20
   const int c = blockIdx.x, tid = threadIdx.x;
   const int B = a.B, N = a.N;
   long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -851,7 +770,7 @@ __global__ void precompose_kernel(const float* __restrict__ wo, const float* __r
 }
 
 constexpr size_t enc_scan_smem() {
-  return ((size_t)(vc::ENC_D + NSLICE) * NCOL + RG * (vc::ENC_D + 4) + 8 * RG * NCOL + RG * NCOL + MAX_ROWS * UPC) * 4;
+  return ((size_t)32 * (vc::ENC_D + 4) + 8 * DEC_XR * NCOL + DEC_XR * NCOL + MAX_ROWS * UPC) * 4;
 }
 constexpr size_t dec_scan_smem() {
   constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + 3 * DEC_XR * NCOL + 2 * DEC_XR * UPC;

@@ -33,13 +33,6 @@ static __device__ __noinline__ void spin_fail(int* err, int code) {
   if (err) atomicExch(err, code);
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > SPIN_TIMEOUT) spin_fail(err, code);
-  }
-}
 // wait and add the stalled cycles to a per-role counter (profiling aid, see vtts_debug_tc_stats)
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc) {
   // mbarrier.try_wait suspends the thread in hardware for a while before it returns false, so the first probe is

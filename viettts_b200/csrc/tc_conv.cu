@@ -105,17 +105,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  const int nprob = L.nprob;
   const int Cin = L.Cin;
   const int nch = Cin / 16;
   const int tiles_per_row = L.tiles_per_row;
   const int ntiles = L.ntiles;
+  const int tiles_per_prob = tiles_per_row * L.B;
 
   // every role walks the same tile sequence
 #define TILE_LOOP_BEGIN                                                        \
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {              \
-    const int pi = tile % nprob;                                               \
-    const int rest = tile / nprob;                                             \
+    const int pi = tile / tiles_per_prob;      /* problems are laid out back to back, most expensive first */ \
+    const int rest = tile - pi * tiles_per_prob;                               \
     const int tt = rest % tiles_per_row;                                       \
     const int b = rest / tiles_per_row;                                        \
     const int tau0 = tt * R;                                                   \
@@ -439,6 +439,9 @@ int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
     for (int ph = 1; ph < NPH; ++ph) { mn = std::min(mn, L.p[i].in_off_ph[ph]); mx = std::max(mx, L.p[i].in_off_ph[ph]); }
     if ((L.p[i].k - 1) * L.p[i].dil + (mx - mn) > 50) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: halo too large");
   }
+  // static round-robin tile assignment: put the expensive problems (large k) first so that the last, partial
+  // wave of tiles consists of cheap ones
+  std::stable_sort(L.p, L.p + L.nprob, [](const TcProb& a, const TcProb& b) { return a.k > b.k; });
   L.tiles_per_row = (L.T_rows + Cfg::R - 1) / Cfg::R;
   L.ntiles = L.nprob * L.tiles_per_row * L.B;
   const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
