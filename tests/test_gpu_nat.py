@@ -172,3 +172,16 @@ def test_mixed_length_bucketed_synthesis(eng, hifigan_params):
         alone = eng.synthesize(tk[None], d[None], n_frames=[n])
         assert wavs[i].shape == (n * 256,)
         assert np.abs(wavs[i] - alone[0]).max() < 1e-5
+
+
+def test_pinned_output_buffer_path(eng, hifigan_params):
+    """`out=` with page-locked memory takes the direct D2H path and must give the same samples."""
+    from viettts_b200.engine import Engine
+    eng.load_hifigan(hifigan_params)
+    tk, d, n = _utt(5, 14, 0.4)
+    ref = eng.synthesize(tk[None], d[None], n_frames=[n], seed=3)
+    buf = Engine.pinned_empty((1, n * 256))
+    got = eng.synthesize(tk[None], d[None], n_frames=[n], seed=3, out=buf)
+    assert got is buf and np.array_equal(got, ref)
+    buf2 = np.empty((1, n * 256), np.float32)           # pageable out= goes through the staging copy
+    assert np.array_equal(eng.synthesize(tk[None], d[None], n_frames=[n], seed=3, out=buf2), ref)

@@ -448,6 +448,17 @@ int vtts_debug_read(vtts_ctx* ctx, const char* name, float* host_out, int64_t n_
 // Layout of the staging areas: inputs first, outputs after, every block 256B aligned; the same
 // offsets are used in the pinned host buffer and in the device staging buffer.
 namespace {
+// true if `p` is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+// results can then be copied D2H straight into the caller's buffer instead of through the context's staging area
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 struct Stager {
   size_t off = 0;
   size_t take(size_t bytes) {
@@ -476,9 +487,10 @@ int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames,
   VTTS_CUDA(cudaMemcpyAsync(dp + o_mel, hp + o_mel, (n_frames ? o_nf + nf_b : mel_b) - o_mel, cudaMemcpyHostToDevice, st));
   rc = vtts_hifigan_forward(ctx, (const float*)(dp + o_mel), n_frames ? (const int32_t*)(dp + o_nf) : nullptr, B, T, (float*)(dp + o_wav), st);
   if (rc) return rc;
-  VTTS_CUDA(cudaMemcpyAsync(hp + o_wav, dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
+  const bool direct = is_pinned_host(wav);
+  VTTS_CUDA(cudaMemcpyAsync(direct ? (void*)wav : (void*)(hp + o_wav), dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
   VTTS_CUDA(cudaStreamSynchronize(st));
-  memcpy(wav, hp + o_wav, wav_b);
+  if (!direct) memcpy(wav, hp + o_wav, wav_b);
   return VTTS_OK;
 }
 
@@ -510,7 +522,9 @@ static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* len
   rc = vtts_acoustic_forward(ctx, (const int32_t*)(dp + o_tok), d_len, (const float*)(dp + o_dur), d_nf,
                              keep_b ? (const uint8_t*)(dp + o_keep) : nullptr, mode, seed, B, L, N, (float*)(dp + o_mel), st);
   if (rc) return rc;
-  if (mel_out) VTTS_CUDA(cudaMemcpyAsync(hp + o_mel, dp + o_mel, mel_b, cudaMemcpyDeviceToHost, st));
+  const bool mel_direct = mel_out && is_pinned_host(mel_out);
+  const bool wav_direct = wav_out && is_pinned_host(wav_out);
+  if (mel_out) VTTS_CUDA(cudaMemcpyAsync(mel_direct ? (void*)mel_out : (void*)(hp + o_mel), dp + o_mel, mel_b, cudaMemcpyDeviceToHost, st));
   if (wav_out) {
     // the hifigan workspace replaces the acoustic one: its kernels are stream-ordered after the acoustic ones,
     // but growing the workspace frees memory -> make sure `mel` (in dstage) is complete first
@@ -518,11 +532,11 @@ static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* len
     if (need > ctx->ws_bytes) VTTS_CUDA(cudaStreamSynchronize(st));
     rc = vtts_hifigan_forward(ctx, (const float*)(dp + o_mel), d_nf, B, N, (float*)(dp + o_wav), st);
     if (rc) return rc;
-    VTTS_CUDA(cudaMemcpyAsync(hp + o_wav, dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
+    VTTS_CUDA(cudaMemcpyAsync(wav_direct ? (void*)wav_out : (void*)(hp + o_wav), dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
   }
   VTTS_CUDA(cudaStreamSynchronize(st));
-  if (mel_out) memcpy(mel_out, hp + o_mel, mel_b);
-  if (wav_out) memcpy(wav_out, hp + o_wav, wav_b);
+  if (mel_out && !mel_direct) memcpy(mel_out, hp + o_mel, mel_b);
+  if (wav_out && !wav_direct) memcpy(wav_out, hp + o_wav, wav_b);
   return VTTS_OK;
 }
 

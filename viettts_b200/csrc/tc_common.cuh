@@ -93,19 +93,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-__device__ __forceinline__ float lrelu(float v, float s) { return v >= 0.f ? v : s * v; }
+// leaky_relu for 0 < s < 1: max(v, s*v) (2 instructions; identical to v >= 0 ? v : s*v for every finite v and +-0)
+__device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, s * v); }
 
-// split 4 floats into packed bf16 hi / lo
+// split 4 floats into packed bf16 hi / lo planes: hi = bf16_rn(v), lo = bf16_rn(v - hi).
+// Packed conversions (cvt.rn.bf16x2.f32) do two values per instruction and deliver the pairs already packed.
 __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                      h3 = __float2bfloat16_rn(v.w);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                      l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
+  const __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
+  const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
+  const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
+  // bf16 -> f32 is a 16-bit shift
+  const float r0 = v.x - __uint_as_float(u01 << 16);
+  const float r1 = v.y - __uint_as_float(u01 & 0xffff0000u);
+  const float r2 = v.z - __uint_as_float(u23 << 16);
+  const float r3 = v.w - __uint_as_float(u23 & 0xffff0000u);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(r0, r1);
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(r2, r3);
+  hi.x = u01;
+  hi.y = u23;
+  lo.x = *reinterpret_cast<const uint32_t*>(&l01);
+  lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
-
 
 }  // namespace tcx

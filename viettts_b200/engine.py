@@ -138,14 +138,16 @@ class Engine:
         self._mel_loaded = True
 
     # ---- host-buffer calls -----------------------------------------------------------
-    def mel2wave(self, mel, n_frames=None) -> np.ndarray:
+    def mel2wave(self, mel, n_frames=None, out=None) -> np.ndarray:
         """mel f32 [B,T,80] -> wav f32 [B,256T] (Generator.__call__, hifigan/model.py:109-125)."""
         mel = _np(mel, np.float32)
         if mel.ndim != 3 or mel.shape[2] != config.MEL_DIM:
             raise ValueError(f"mel must be [B,T,{config.MEL_DIM}], got {mel.shape}")
         B, T, _ = mel.shape
         nf = None if n_frames is None else _np(n_frames, np.int32, (B,), "n_frames")
-        wav = np.empty((B, T * config.HOP), np.float32)
+        if out is not None and (out.shape != (B, T * config.HOP) or out.dtype != np.float32 or not out.flags.c_contiguous):
+            raise ValueError(f"out must be C-contiguous float32 {(B, T * config.HOP)}")
+        wav = out if out is not None else np.empty((B, T * config.HOP), np.float32)
         self._ck(self.lib.vtts_mel2wave_host(self.h, _ptr(mel), _ptr(nf), B, T, _ptr(wav)))
         return wav
 
@@ -193,11 +195,30 @@ class Engine:
             mel[sl] = out
         return mel
 
-    def synthesize(self, tokens, dur_frames, lengths=None, n_frames=None, masks=None, seed=None, return_mel=False):
+    @staticmethod
+    def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+        """numpy array backed by page-locked host memory.  Passed as `out=` to synthesize / mel2wave the
+        library copies D2H straight into it (no staging copy, no page faults of a fresh array)."""
+        import torch
+        t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        a = t.numpy()
+        Engine._pinned_keepalive[a.ctypes.data] = t   # the tensor owns the memory
+        return a
+
+    _pinned_keepalive: dict = {}
+
+    def synthesize(self, tokens, dur_frames, lengths=None, n_frames=None, masks=None, seed=None, return_mel=False, out=None):
         """predict_mel -> mel2wave with the mel staying on the device.  Returns wav [B,256N]
-        (and mel [B,N,80] if return_mel)."""
+        (and mel [B,N,80] if return_mel).  `out`: optional preallocated float32 [B,256N] result array
+        (ideally from `pinned_empty`)."""
         tokens, dur, lens, nf, N, masks, mode, seed = self._acoustic_args(tokens, dur_frames, lengths, n_frames, masks, seed)
         B, L = tokens.shape
+        if out is not None and B <= MAX_ACOUSTIC_ROWS and not return_mel:
+            if out.shape != (B, N * config.HOP) or out.dtype != np.float32 or not out.flags.c_contiguous:
+                raise ValueError(f"out must be C-contiguous float32 {(B, N * config.HOP)}")
+            self._ck(self.lib.vtts_synthesize_host(
+                self.h, _ptr(tokens), _ptr(lens), _ptr(dur), _ptr(nf), _ptr(masks), mode, seed, B, L, N, None, _ptr(out)))
+            return out
         wav = np.empty((B, N * config.HOP), np.float32)
         mel = np.empty((B, N, config.MEL_DIM), np.float32) if return_mel else None
         for b0 in range(0, B, MAX_ACOUSTIC_ROWS):
