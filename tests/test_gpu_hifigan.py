@@ -97,3 +97,16 @@ def test_bad_arguments_raise(eng):
     with pytest.raises(VttsError):
         e2.mel2wave(np.zeros((1, 4, 80), np.float32))   # weights not loaded
     e2.close()
+
+
+def test_long_utterance_vs_oracle(hifigan_params):
+    """Maximum-size style case: 1 000 mel frames (16 s) in one row, both arithmetic paths."""
+    from viettts_b200.engine import Engine
+    e = Engine(0)
+    e.load_hifigan(hifigan_params)
+    mel = synthetic.mel_input(99, 1, 1000)
+    ref = ho.mel2wave(hifigan_params, mel).reshape(1, -1)
+    for mode in ("fp32", "bf16x3"):
+        e.set_precision(mode)
+        _cmp(e.mel2wave(mel), ref, f"T=1000 {mode}")
+    e.close()

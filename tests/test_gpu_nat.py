@@ -185,3 +185,31 @@ def test_pinned_output_buffer_path(eng, hifigan_params):
     assert got is buf and np.array_equal(got, ref)
     buf2 = np.empty((1, n * 256), np.float32)           # pageable out= goes through the staging copy
     assert np.array_equal(eng.synthesize(tk[None], d[None], n_frames=[n], seed=3, out=buf2), ref)
+
+
+def test_batch_spanning_two_decoder_launches(eng, acoustic_ckpt):
+    """40 rows = two launches of the 32-row scan kernel: rows must not depend on their launch."""
+    B = 40
+    utts = [_utt(300 + b, 24, 0.6) for b in range(B)]
+    L = 24
+    tokens = np.stack([u[0] for u in utts])
+    dur = np.stack([u[1] for u in utts])
+    nfs = np.array([u[2] for u in utts], np.int32)
+    masks = synthetic.dropout_masks(17, B, int(nfs.max()))
+    mel = eng.predict_mel(tokens, dur, n_frames=nfs, masks=masks)
+    for b in (0, 31, 32, 39):
+        ref = no.inference(acoustic_ckpt, tokens[b : b + 1], dur[b : b + 1], int(nfs[b]), masks[b : b + 1, : nfs[b]]).numpy()
+        assert np.abs(mel[b, : nfs[b]] - ref[0]).max() < MEL_LINF
+        assert np.all(mel[b, nfs[b] :] == 0.0)
+
+
+def test_long_utterance_300_phonemes(eng, acoustic_ckpt):
+    """Upper end of BASELINE configs[4]: 300 phonemes, 937 frames (upsampling shared memory, long scan)."""
+    tk, d, n = _utt(77, 300, 15.0)
+    assert n >= 930
+    masks = synthetic.dropout_masks(4, 1, n)
+    mel = eng.predict_mel(tk[None], d[None], n_frames=[n], masks=masks)
+    ref = no.inference(acoustic_ckpt, tk[None], d[None], n, masks, dtype=torch.float64).numpy()
+    err = np.abs(mel - ref).max()
+    print(f"L=300 N={n}: err {err:.3e}")
+    assert err < MEL_LINF
