@@ -11,7 +11,9 @@ names = ["mma_total", "mma_wait_tmem", "mma_wait_A", "mma_wait_W", "prod_wait_sl
 import os
 VAR = int(os.environ.get("TCV", "0"))
 CASES = [(32, 7, 1, 2_560_000, True), (32, 7, 1, 2_560_000, False), (64, 7, 1, 1_280_000, True), (128, 7, 1, 640_000, True), (128, 7, 1, 640_000, False), (256, 7, 1, 80_000, True)]
-if VAR:
+if VAR == 3:
+    CASES = [(32, 3, 1, 2_560_000, True), (32, 7, 1, 2_560_000, True), (32, 11, 1, 2_560_000, True), (64, 3, 1, 1_280_000, True), (64, 7, 1, 1_280_000, True), (64, 11, 1, 1_280_000, True)]
+elif VAR:
     CASES = [(128, 3, 1, 640_000, True), (128, 7, 1, 640_000, True), (128, 7, 1, 640_000, False), (128, 11, 1, 640_000, True), (256, 3, 1, 160_000, True), (256, 7, 1, 160_000, True), (256, 7, 1, 160_000, False)]
 for C, k, dil, rows, resid in CASES:
     B = 32

@@ -15,8 +15,9 @@
 //   B operand: weights pre-split and pre-packed at load time into the same canonical layout,
 //     streamed with cp.async.bulk (TMA bulk copy) through a 4-stage mbarrier ring.
 //
-// One persistent CTA per SM, 14 warps:
-//   warps 0-3  epilogue   tcgen05.ld TMEM -> regs, + bias (+ residual), fp32 NWC store
+// One persistent CTA per SM, 18 warps:
+//   warps 0-3, 14-17  epilogue (two groups, alternate 32-column chunks): tcgen05.ld TMEM -> regs -> smem slab ->
+//              coalesced + bias (+ BN/act) (+ residual) fp32 NWC store
 //   warp  4    MMA issue  (one lane) + TMEM alloc/dealloc
 //   warp  5    weight producer (one lane, cp.async.bulk + expect_tx)
 //   warps 6-13 activation converters: fp32 global -> [mean3] -> leaky_relu -> hi/lo bf16 -> smem
@@ -35,7 +36,9 @@ using namespace tcx;
 
 constexpr int NA = 4;               // activation stages
 constexpr int NW_MAX = 8;            // weight stages: 6 x 16 KB for N = 256, 8 smaller ones otherwise (covers the L2 latency)
-constexpr int NTHREADS = 448;     // 4 epilogue + MMA + weight producer + 8 converter warps
+constexpr int COLL = 1;          // A-operand collector reuse between the a_hi x W_hi and a_hi x W_lo MMAs
+constexpr int NTHREADS = 576;     // 4 epilogue + MMA + weight producer + 8 converter + 4 more epilogue warps
+constexpr int NEPI = 256;         // epilogue threads (two groups of 4 warps; warp % 4 = TMEM lane quadrant)
 constexpr int NCONV = 256;        // converter threads
 constexpr int NGRP = 2;           // independent converter groups (alternate chunks -> two chunks in flight)
 constexpr int GRP_THREADS = NCONV / NGRP;
@@ -61,7 +64,7 @@ struct TcCfg {
   static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : (TMEM_RAW <= 64 ? 64 : (TMEM_RAW <= 128 ? 128 : (TMEM_RAW <= 256 ? 256 : 512)));
   static constexpr int NBAR = 2 * NA + 2 * NW + 2 * NACC;
   static constexpr int EPI_PITCH = 144;                      // bytes per staged row: 32 floats + 16 B pad (conflict-free)
-  static constexpr int EPI_STAGE = 4 * 32 * EPI_PITCH;       // one 32-row slab per epilogue warp
+  static constexpr int EPI_STAGE = 8 * 32 * EPI_PITCH;       // one 32-row slab per epilogue warp
   static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_STAGE + EPI_STAGE + NBAR * 8 + 16 + 1024;
 };
 
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   if (warp == 5 && lane == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], GRP_THREADS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
                     umma(d, a_hi, b_hi, idesc2, first);     // [main | aux] (+)= A_hi . [W_hi | W_lo]
                     umma(d, a_lo, b_hi, idesc, 1u);         // main += A_lo . W_hi
                   } else {
-                    umma(d, a_hi, b_hi, idesc, first);
-                    umma(d, a_hi, b_lo, idesc, 1u);
+                    umma<COLL ? 1 : 0>(d, a_hi, b_hi, idesc, first);
+                    umma<COLL ? 2 : 0>(d, a_hi, b_lo, idesc, 1u);
                     umma(d, a_lo, b_hi, idesc, 1u);
                   }
                 }
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       if (L.dbg) L.dbg[(size_t)blockIdx.x * 16 + 4] = w_e;
     }
     __syncwarp();
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && warp < 14) {
     // ============================ activation converters ============================
     // Two groups of 4 warps; group g fills the chunks with (global chunk counter) % 2 == g, so one group's
     // memory round trip overlaps the other's convert+store phase.
@@ -294,24 +297,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     TILE_LOOP_END
     if (L.dbg && gt == 0) { L.dbg[(size_t)blockIdx.x * 16 + 5 + 4 * grp] = w_ae; L.dbg[(size_t)blockIdx.x * 16 + 6 + 4 * grp] = t_fill; }
   } else {
-    // ============================ epilogue (warps 0-3) ============================
+    // ============================ epilogue (warps 0-3 and 14-17) ============================
     // TMEM -> registers (thread = row) -> per-warp padded smem slab -> registers (8 lanes = one 128 B row
-    // segment) so that the residual loads and the stores are fully coalesced; residuals of the next
-    // 32-column chunk are prefetched while the current one drains.
+    // segment) so that the residual loads and the stores are fully coalesced.  Two groups of four warps take
+    // alternate 32-column chunks; each group prefetches the residuals of its next chunk.
+    const int eg = warp >= 14 ? 1 : 0;      // epilogue group
+    const int quad = warp & 3;              // TMEM lane quadrant of this warp
     uint32_t acc = 0, tph = 0;
     const int out_ld = L.out_ld;
     long long w_tf = 0, t_epi = 0;
-    uint8_t* slab = epi_st + warp * (32 * Cfg::EPI_PITCH);
+    uint8_t* slab = epi_st + (eg * 4 + quad) * (32 * Cfg::EPI_PITCH);
     const int trow = lane >> 3;          // 0..3   row inside a group of 4
     const int tch = lane & 7;            // 16 B chunk inside the 128 B row segment
     constexpr int NCHUNK = N / 32;
+    constexpr int NIT = NPH * MT * NCHUNK;
     const int n_valid = (EPI && L.n_valid > 0) ? L.n_valid : N;
     const int post_act = EPI ? L.post_act : 0;
     TILE_LOOP_BEGIN
       const size_t out_base = (size_t)b * L.rows_out * out_ld;
       const int ostride = P.out_stride;
       const float* __restrict__ resid = P.resid;
-      const int row_w = tau0 + warp * 32;          // first row of this warp inside M-tile 0
+      const int row_w = tau0 + quad * 32;          // first row of this warp inside M-tile 0
       float4 rs[8];
       auto load_resid = [&](int it, float4 (&dst)[8]) {
         const int pm = it / NCHUNK, c0 = (it - pm * NCHUNK) * 32;
@@ -324,25 +330,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             dst[s8] = __ldg(reinterpret_cast<const float4*>(resid + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4));
         }
       };
-      load_resid(0, rs);
+      if (eg < NIT) load_resid(eg, rs);
       mbar_wait_t(&tmem_full[acc], tph, L.err, 6, w_tf);
       const long long te0 = clock64();
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * Cfg::ACC_COLS;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Cfg::ACC_COLS;
 #pragma unroll 1
-      for (int it = 0; it < NPH * MT * NCHUNK; ++it) {
+      for (int it = eg; it < NIT; it += 2) {
         const int pm = it / NCHUNK, c0 = (it - pm * NCHUNK) * 32;
         const int mt = pm % MT, ooff = P.out_off_ph[pm / MT];
-        uint32_t r[32];
-        tmem_ld16(taddr0 + pm * DW + c0, r);
-        tmem_ld16(taddr0 + pm * DW + c0 + 16, r + 16);
-        uint32_t r2[STK ? 32 : 1];
-        if constexpr (STK) {
-          tmem_ld16(taddr0 + pm * DW + N + c0, r2);
-          tmem_ld16(taddr0 + pm * DW + N + c0 + 16, r2 + 16);
+        {
+          uint32_t r[32];
+          tmem_ld16(taddr0 + pm * DW + c0, r);
+          tmem_ld16(taddr0 + pm * DW + c0 + 16, r + 16);
+          if constexpr (STK) {
+            uint32_t r2[32];
+            tmem_ld16(taddr0 + pm * DW + N + c0, r2);
+            tmem_ld16(taddr0 + pm * DW + N + c0 + 16, r2 + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(r2[q]));
+          } else {
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(slab + lane * Cfg::EPI_PITCH + q * 16) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
         }
+        __syncwarp();
+        // the accumulator registers are dead now: prefetch the residuals of this group's next chunk
         float4 rs_next[8];
-        if (it + 1 < NPH * MT * NCHUNK) load_resid(it + 1, rs_next);
+        if (it + 2 < NIT) load_resid(it + 2, rs_next);
         const bool col_ok = !EPI || (c0 + tch * 4 < n_valid);
         float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), mu = bi, iv = make_float4(1.f, 1.f, 1.f, 1.f), of = bi;
         if (col_ok) {
@@ -353,15 +371,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             of = __ldg(reinterpret_cast<const float4*>(P.bn_off + c0 + tch * 4));
           }
         }
-        tmem_ld_wait();
-        if constexpr (STK) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(r2[q]));
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(slab + lane * Cfg::EPI_PITCH + q * 16) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-        __syncwarp();
 #pragma unroll
         for (int s8 = 0; s8 < 8; ++s8) {
           const int rl = s8 * 4 + trow;
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             *reinterpret_cast<float4*>(P.out + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4) = o;
         }
         __syncwarp();
-        if (it + 1 < NPH * MT * NCHUNK) {
+        if (it + 2 < NIT) {
 #pragma unroll
           for (int s8 = 0; s8 < 8; ++s8) rs[s8] = rs_next[s8];
         }
