@@ -10,6 +10,8 @@
  *   vietTTS/nat/dsp.py:104-128            MelFilter(...)(y)        -> vtts_melspec_host / vtts_melspec
  *   vietTTS/hifigan/mel2wave.py:35-36     pickle.load(hk_hifi)     -> vtts_load_hifigan
  *   vietTTS/nat/text2mel.py:62-71         pickle.load(acoustic)    -> vtts_load_acoustic
+ *   vietTTS/nat/text2mel.py:22-34         predict_duration(tokens) -> vtts_predict_duration_host / vtts_duration_forward
+ *   vietTTS/nat/text2mel.py:27-28         pickle.load(duration)    -> vtts_load_duration
  *
  * Conventions
  *   - plain C types only; no torch / CUDA types in signatures (`stream` is a
@@ -74,8 +76,10 @@ int vtts_get_precision(vtts_ctx* ctx);
  * weights received by an NCCL broadcast without a host round trip. */
 int64_t vtts_hifigan_blob_floats(void);                  /* 13 926 017 */
 int64_t vtts_acoustic_blob_floats(void);                 /* params + BatchNorm eval statistics */
+int64_t vtts_duration_blob_floats(void);                 /* TokenEncoder block of the acoustic blob + projection head */
 int vtts_load_hifigan(vtts_ctx* ctx, const float* blob, int64_t n_floats);
 int vtts_load_acoustic(vtts_ctx* ctx, const float* blob, int64_t n_floats);
+int vtts_load_duration(vtts_ctx* ctx, const float* blob, int64_t n_floats);
 /* librosa-style filterbank [80][513] (MelFilter.__init__, dsp.py:107-113) */
 int vtts_load_mel_filterbank(vtts_ctx* ctx, const float* fb, int n_mels, int n_bins);
 
@@ -97,12 +101,19 @@ int vtts_acoustic_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_
                           const uint8_t* keep_mask_dev, int dropout_mode, uint64_t seed,
                           int B, int L, int N, float* mel_dev, void* stream);
 
+/* DurationModel.__call__ (vietTTS/nat/model.py:64-70, is_training=False): TokenEncoder -> Linear(256) -> gelu(tanh
+ * form, the jax default) -> Linear(1) -> softplus.  tokens_dev int32 [B,L]; lengths_dev int32 [B] or NULL (= L);
+ * dur_sec_dev [B,L] predicted durations in SECONDS (0 past lengths[b]).  Row b equals the reference run on row b alone.
+ * The silence clip / word-end zeroing of text2mel (text2mel.py:88-97) is host logic (viettts_b200/nat/text2mel.py). */
+int vtts_duration_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev, int B, int L,
+                          float* dur_sec_dev, void* stream);
+
 /* MelFilter.__call__ (vietTTS/nat/dsp.py:115-128). wav_dev [B,S], S % 256 == 0, S >= 512;
  * mel_dev [B,S/256,80]. */
 int vtts_melspec(vtts_ctx* ctx, const float* wav_dev, int B, int S, float* mel_dev, void* stream);
 
 /* optional taps for tests: copy an internal activation of the LAST forward call to host.
- * name: "enc" [B,L,512], "cond" [B,N,512], "mel_pre" [B,N,80] (before the postnet). */
+ * name: "enc" [B,L,512] (of the last acoustic OR duration call), "cond" [B,N,512], "mel_pre" [B,N,80] (before the postnet). */
 int vtts_debug_read(vtts_ctx* ctx, const char* name, float* host_out, int64_t n_floats);
 
 /* test hook: one hk.Conv1D (SAME padding, dilation, optional leaky_relu on the input and residual
@@ -130,18 +141,30 @@ int vtts_predict_mel_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* l
                           const float* dur_frames, const int32_t* n_frames,
                           const uint8_t* keep_mask, int dropout_mode, uint64_t seed,
                           int B, int L, int N, float* mel);
+int vtts_predict_duration_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float* dur_sec);
 /* predict_mel -> mel2wave without leaving the device: tokens/durations in, waveform out */
 int vtts_synthesize_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths,
                          const float* dur_frames, const int32_t* n_frames,
                          const uint8_t* keep_mask, int dropout_mode, uint64_t seed,
                          int B, int L, int N, float* mel_out_or_null, float* wav);
+/* text2mel (vietTTS/nat/text2mel.py:85-103) + mel2wave (synthesizer.py:36-37) for a batch of token rows in one call:
+ * predicted durations -> silence tokens clipped from below at silence_duration, word-end tokens 0 s -> frames ->
+ * AcousticModel.inference -> trailing-silence frames cut -> Generator.
+ * tokens int32 [B,L]; lengths int32 [B] or NULL; dropout_mode OFF or SEED.  Outputs: dur_sec_out [B,L] adjusted
+ * durations in seconds (may be NULL); n_frames_out int32 [B] frames of each row's waveform; *n_max_out = row pitch in
+ * frames; wav = dense [B][256 * n_max] (samples past 256*n_frames_out[b] are 0), capacity B*256*max_frames floats.
+ * If n_max > max_frames nothing is synthesized: the call fails with VTTS_ERR_BAD_ARG after setting *n_max_out and
+ * n_frames_out, so the caller can retry with a buffer of that size. */
+int vtts_tts_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float silence_duration,
+                  int dropout_mode, uint64_t seed, int max_frames, float* dur_sec_out, int32_t* n_frames_out,
+                  int32_t* n_max_out, float* wav);
 int vtts_melspec_host(vtts_ctx* ctx, const float* wav, int B, int S, float* mel);
 
 /* ---- introspection for bench / tests ------------------------------------------------------ */
 /* number of kernel launches issued by this context since creation (our kernels only) */
 int64_t vtts_launch_count(vtts_ctx* ctx);
 /* elapsed ms of the last forward call of the given stage, measured with CUDA events on the
- * stream the kernels were launched on: stage 0 = hifigan, 1 = acoustic, 2 = melspec.
+ * stream the kernels were launched on: stage 0 = hifigan, 1 = acoustic, 2 = melspec, 3 = duration.
  * Synchronises the stream. */
 int vtts_last_stage_ms(vtts_ctx* ctx, int stage, float* ms);
 

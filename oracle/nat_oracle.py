@@ -12,6 +12,8 @@ arbiter for the float32 CUDA path.
   AcousticModel.postnet      vietTTS/nat/model.py:113-121
   AcousticModel.inference    vietTTS/nat/model.py:123-144
   predict_mel                vietTTS/nat/text2mel.py:61-82
+  DurationModel.__call__     vietTTS/nat/model.py:49-70
+  text2mel post-processing   vietTTS/nat/text2mel.py:85-103
 
 dm-haiku semantics used (not vendored in the reference, setup.py:6-19):
   hk.LSTM            z=[x,h]W+b; i,g,f,o=split(z,4); c'=sigmoid(f+1)c+sigmoid(i)tanh(g); h'=sigmoid(o)tanh(c')
@@ -61,9 +63,9 @@ def lstm_step(x, h, c, w, b):
     return h, c
 
 
-def token_encoder(P, S, tokens, lengths, dtype=torch.float32):
+def token_encoder(P, S, tokens, lengths, dtype=torch.float32, T=T):
     """model.py:26-47 with is_training=False.  tokens int [B,L]; lengths int [B].
-    Returns [B,L,2D]."""
+    Returns [B,L,2D].  `T` is the Haiku module prefix (acoustic or duration model's encoder)."""
     tokens = torch.as_tensor(np.asarray(tokens)).long()
     lengths = torch.as_tensor(np.asarray(lengths)).long()
     x = _t(P[T + "embed"]["embeddings"], dtype)[tokens]
@@ -194,3 +196,55 @@ def inference_ragged(ckpt, tokens_list, dur_frames_list, masks_list=None, dtype=
         m = None if masks_list is None else np.asarray(masks_list[b])[None, :n]
         outs.append(inference(ckpt, np.asarray(tk, np.int32)[None, :], d, n, m, dtype)[0].numpy())
     return outs
+
+
+# ---------------------------------------------------------------------------
+# DurationModel (model.py:49-70) and the text2mel glue around it (text2mel.py:85-103)
+# ---------------------------------------------------------------------------
+DM = "duration_model/~/"
+
+
+def gelu_tanh(x):
+    """jax.nn.gelu with its default approximate=True (model.py:61 passes the bare function)."""
+    return 0.5 * x * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * x ** 3)))
+
+
+def softplus(x):
+    """jax.nn.softplus = logaddexp(x, 0)."""
+    return torch.clamp(x, min=0) + torch.log1p(torch.exp(-torch.abs(x)))
+
+
+def duration_model(ckpt, tokens, lengths, dtype=torch.float32):
+    """DurationModel(is_training=False)(DurationInput(tokens, lengths, None)), model.py:64-70.
+    tokens int [B,L]; lengths int [B] -> durations in seconds [B,L] (every position, as the reference)."""
+    P, S = ckpt["params"], ckpt["aux"]
+    with torch.no_grad():
+        x = token_encoder(P, S, tokens, lengths, dtype, T=DM + "token_encoder/~/")
+        l1, l2 = P[DM + "linear"], P[DM + "linear_1"]
+        x = gelu_tanh(x @ _t(l1["w"], dtype) + _t(l1["b"], dtype))
+        x = (x @ _t(l2["w"], dtype) + _t(l2["b"], dtype)).squeeze(-1)
+        return softplus(x).numpy()
+
+
+def predict_duration(ckpt, tokens, dtype=torch.float32):
+    """text2mel.py:22-34: one utterance, lengths = [len(tokens)] -> [1,L] seconds."""
+    tok = np.asarray(tokens, np.int32)[None, :]
+    return duration_model(ckpt, tok, np.array([tok.shape[1]], np.int32), dtype)
+
+
+def adjust_durations(tokens, durations, silence_duration=-1.0, sil_index=0, word_end_index=3):
+    """text2mel.py:88-97: sil tokens are clipped from below at `silence_duration`, word-end tokens get 0."""
+    tok = np.asarray(tokens)[None, :]
+    d = np.asarray(durations, np.float32)
+    d = np.where(tok == sil_index, np.clip(d, silence_duration, None), d)
+    d = np.where(tok == word_end_index, np.float32(0.0), d)
+    return d.astype(np.float32)
+
+
+def trim_end_silence(tokens, durations, mel, sil_index=0):
+    """text2mel.py:99-102: drop the frames of the trailing silence token."""
+    if tokens[-1] == sil_index:
+        end_silence = float(durations[0, -1])
+        silence_frame = int(end_silence * 16000 / 256)
+        mel = mel[:, : (mel.shape[1] - silence_frame)]
+    return mel

@@ -32,7 +32,11 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "vtts_hifigan_blob_floats": (C.c_int64, []),
     "vtts_acoustic_blob_floats": (C.c_int64, []),
+    "vtts_duration_blob_floats": (C.c_int64, []),
     "vtts_load_hifigan": (C.c_int, [c_ctx, C.c_void_p, C.c_int64]),
+    "vtts_load_duration": (C.c_int, [c_ctx, C.c_void_p, C.c_int64]),
+    "vtts_duration_forward": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vtts_predict_duration_host": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtts_load_acoustic": (C.c_int, [c_ctx, C.c_void_p, C.c_int64]),
     "vtts_load_mel_filterbank": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int]),
     "vtts_hifigan_forward": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -45,6 +49,8 @@ SIGNATURES = {
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtts_synthesize_host": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
                                        C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vtts_tts_host": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64, C.c_int,
+                                C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "vtts_melspec_host": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtts_launch_count": (C.c_int64, [c_ctx]),
     "vtts_last_stage_ms": (C.c_int, [c_ctx, C.c_int, C.POINTER(C.c_float)]),

@@ -35,6 +35,14 @@ SIL_INDEX = 0
 WORD_END_INDEX = 3
 N_NORMAL_PHONEMES = 89       # len(FLAGS._normal_phonemes)
 ALPHABET_SIZE = len(SPECIAL_PHONEMES) + N_NORMAL_PHONEMES  # 93
+# the 89 letters of FLAGS._normal_phonemes, in the reference's order (token id = 4 + position)
+NORMAL_PHONEMES = list(
+    "abcdeghiklmnopqrstuvxy"
+    "àáâãèéêìíòóôõùúýăđĩũơư"
+    "ạảấầẩẫậắằẳẵặẹẻẽếềểễệỉịọỏốồổỗộớờởỡợụủứừửữựỳỵỷỹ"
+)
+assert len(NORMAL_PHONEMES) == N_NORMAL_PHONEMES
+PHONEMES = SPECIAL_PHONEMES + NORMAL_PHONEMES   # data_loader.py:11-13 load_phonemes_set()
 
 # ---- assets/hifigan/config.json --------------------------------------------
 HIFIGAN = dict(
@@ -55,6 +63,8 @@ HIFIGAN_KEYS_CHECKED = tuple(HIFIGAN.keys())
 HIFIGAN_CONFIG_FILE = Path("assets/hifigan/config.json")
 HIFIGAN_CKPT = Path("assets/infore/hifigan/hk_hifi.pickle")
 ACOUSTIC_CKPT = Path("assets/infore/nat/acoustic_latest_ckpt.pickle")
+DURATION_CKPT = Path("assets/infore/nat/duration_latest_ckpt.pickle")   # text2mel.py:27
+LEXICON_FILE = Path("train_data/lexicon.txt")                           # text2mel.py:86 (FLAGS.data_dir / "lexicon.txt")
 
 # analytical work figures (SURVEY.md §8d / BASELINE.md §3) used by bench.py
 HIFIGAN_MAC_PER_FRAME = 307_052_544

@@ -134,6 +134,19 @@ const std::vector<TensorSpec>& vtts_acoustic_specs() {
   return s;
 }
 
+// duration checkpoint: the TokenEncoder tensors in the acoustic blob's order, then the projection head
+const std::vector<TensorSpec>& vtts_duration_specs() {
+  static std::vector<TensorSpec> s;
+  if (!s.empty()) return s;
+  const std::vector<TensorSpec>& a = vtts_acoustic_specs();
+  for (int i = 0; i <= aci::ENC_LSTM_B_B; ++i) s.push_back(a[i]);
+  s.push_back({"proj.fc1.w[512,256]", 512 * 256});
+  s.push_back({"proj.fc1.b", 256});
+  s.push_back({"proj.fc2.w[256,1]", 256});
+  s.push_back({"proj.fc2.b", 1});
+  return s;
+}
+
 static int64_t total_floats(const std::vector<TensorSpec>& s) {
   int64_t t = 0;
   for (auto& e : s) t += e.n;
@@ -212,7 +225,7 @@ int vtts_create(int device, vtts_ctx** out) {
     delete ctx;
     return VTTS_ERR_CUDA;
   }
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < vtts_ctx::NSTAGE; ++i) {
     cudaEventCreate(&ctx->ev0[i]);
     cudaEventCreate(&ctx->ev1[i]);
   }
@@ -236,10 +249,11 @@ int vtts_destroy(vtts_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   cudaFree(ctx->hg_blob); cudaFree(ctx->hg_upsw); cudaFree(ctx->ac_blob); cudaFree(ctx->ac_derived);
+  cudaFree(ctx->du_blob); cudaFree(ctx->du_derived); cudaFree(ctx->du_wpk);
   cudaFree(ctx->mel_fb); cudaFree(ctx->mel_lo); cudaFree(ctx->mel_hi); cudaFree(ctx->fft_tw); cudaFree(ctx->hann);
   cudaFree(ctx->ws); cudaFree(ctx->dstage); cudaFree(ctx->d_err); cudaFree(ctx->hg_wpk); cudaFree(ctx->ac_wpk); cudaFree(ctx->d_tc_dbg);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < vtts_ctx::NSTAGE; ++i) {
     cudaEventDestroy(ctx->ev0[i]);
     cudaEventDestroy(ctx->ev1[i]);
   }
@@ -339,6 +353,7 @@ int vtts_debug_pair(vtts_ctx* ctx, const float* x_dev, const float* w1_dev, cons
 
 int64_t vtts_hifigan_blob_floats(void) { return total_floats(vtts_hifigan_specs()); }
 int64_t vtts_acoustic_blob_floats(void) { return total_floats(vtts_acoustic_specs()); }
+int64_t vtts_duration_blob_floats(void) { return total_floats(vtts_duration_specs()); }
 
 int vtts_load_hifigan(vtts_ctx* ctx, const float* blob, int64_t n_floats) {
   if (!ctx) return VTTS_ERR_BAD_ARG;
@@ -361,6 +376,18 @@ int vtts_load_acoustic(vtts_ctx* ctx, const float* blob, int64_t n_floats) {
   rc = vtts_acoustic_prepare(ctx);
   if (rc) return rc;
   ctx->ac_loaded = true;
+  return VTTS_OK;
+}
+
+int vtts_load_duration(vtts_ctx* ctx, const float* blob, int64_t n_floats) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  ctx->du_loaded = false;
+  int rc = load_blob(ctx, vtts_duration_specs(), blob, n_floats, &ctx->du_blob, ctx->du_t);
+  if (rc) return rc;
+  rc = vtts_duration_prepare(ctx);
+  if (rc) return rc;
+  ctx->du_loaded = true;
   return VTTS_OK;
 }
 
@@ -415,6 +442,23 @@ int vtts_acoustic_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_
   rc = vtts_acoustic_run(ctx, tokens_dev, lengths_dev, dur_frames_dev, n_frames_dev, keep_mask_dev, dropout_mode, seed, B, L, N,
                          mel_dev, st, ctx->ws, ctx->ws_bytes, nullptr);
   stage_end(ctx, 1, st);
+  return rc;
+}
+
+int vtts_duration_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev, int B, int L, float* dur_sec_dev,
+                          void* stream) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!tokens_dev || !dur_sec_dev) return ctx->fail(VTTS_ERR_BAD_ARG, "duration_forward: null pointer");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need = 0;
+  int rc = vtts_duration_run(ctx, nullptr, nullptr, B, L, nullptr, st, nullptr, 0, &need);
+  if (rc) return rc;
+  rc = ctx->ensure_ws(need);
+  if (rc) return rc;
+  stage_begin(ctx, 3, st);
+  rc = vtts_duration_run(ctx, tokens_dev, lengths_dev, B, L, dur_sec_dev, st, ctx->ws, ctx->ws_bytes, nullptr);
+  stage_end(ctx, 3, st);
   return rc;
 }
 
@@ -495,7 +539,10 @@ int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames,
 }
 
 static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur, const int32_t* n_frames,
-                        const uint8_t* keep, int mode, uint64_t seed, int B, int L, int N, float* mel_out, float* wav_out) {
+                        const uint8_t* keep, int mode, uint64_t seed, int B, int L, int N, float* mel_out, float* wav_out,
+                        const int32_t* n_frames_voc = nullptr) {
+  // n_frames_voc: optional per-row frame counts for the generator only (text2mel trims the trailing silence from the
+  // mel AFTER the postnet, text2mel.py:99-102); default = n_frames
   if (!tokens || !dur || B < 1 || L < 1 || N < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "predict_mel/synthesize_host: bad argument");
   if (mode == VTTS_DROPOUT_MASK && !keep) return ctx->fail(VTTS_ERR_BAD_ARG, "dropout_mode MASK needs keep_mask");
   VTTS_CUDA(cudaSetDevice(ctx->device));
@@ -504,6 +551,7 @@ static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* len
   const size_t keep_b = mode == VTTS_DROPOUT_MASK ? (size_t)B * N * 2 * vc::PRENET : 0;
   const size_t mel_b = (size_t)B * N * vc::MEL * 4, wav_b = wav_out ? (size_t)B * N * vc::HOP * 4 : 0;
   const size_t o_tok = s.take(tok_b), o_len = s.take(len_b), o_dur = s.take(dur_b), o_nf = s.take(nf_b), o_keep = s.take(keep_b);
+  const size_t o_nfv = s.take(n_frames_voc ? nf_b : 0);
   const size_t in_end = s.off;
   const size_t o_mel = s.take(mel_b), o_wav = s.take(wav_b);
   int rc = ctx->ensure_staging(s.off, s.off);
@@ -516,6 +564,7 @@ static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* len
   memcpy(hp + o_dur, dur, dur_b);
   if (n_frames) memcpy(hp + o_nf, n_frames, nf_b);
   if (keep_b) memcpy(hp + o_keep, keep, keep_b);
+  if (n_frames_voc) memcpy(hp + o_nfv, n_frames_voc, nf_b);
   VTTS_CUDA(cudaMemcpyAsync(dp, hp, in_end, cudaMemcpyHostToDevice, st));
   const int32_t* d_len = lengths ? (const int32_t*)(dp + o_len) : nullptr;
   const int32_t* d_nf = n_frames ? (const int32_t*)(dp + o_nf) : nullptr;
@@ -530,7 +579,8 @@ static int synth_common(vtts_ctx* ctx, const int32_t* tokens, const int32_t* len
     // but growing the workspace frees memory -> make sure `mel` (in dstage) is complete first
     size_t need = vtts_hifigan_ws_bytes(B, N);
     if (need > ctx->ws_bytes) VTTS_CUDA(cudaStreamSynchronize(st));
-    rc = vtts_hifigan_forward(ctx, (const float*)(dp + o_mel), d_nf, B, N, (float*)(dp + o_wav), st);
+    rc = vtts_hifigan_forward(ctx, (const float*)(dp + o_mel), n_frames_voc ? (const int32_t*)(dp + o_nfv) : d_nf, B, N,
+                              (float*)(dp + o_wav), st);
     if (rc) return rc;
     VTTS_CUDA(cudaMemcpyAsync(wav_direct ? (void*)wav_out : (void*)(hp + o_wav), dp + o_wav, wav_b, cudaMemcpyDeviceToHost, st));
   }
@@ -554,6 +604,81 @@ int vtts_synthesize_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* le
   if (!ctx) return VTTS_ERR_BAD_ARG;
   if (!wav) return ctx->fail(VTTS_ERR_BAD_ARG, "synthesize_host: null output");
   return synth_common(ctx, tokens, lengths, dur_frames, n_frames, keep_mask, dropout_mode, seed, B, L, N, mel_out_or_null, wav);
+}
+
+int vtts_predict_duration_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float* dur_sec) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!tokens || !dur_sec || B < 1 || L < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "predict_duration_host: bad argument");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  Stager s;
+  const size_t tok_b = (size_t)B * L * 4, len_b = (size_t)B * 4, dur_b = (size_t)B * L * 4;
+  const size_t o_tok = s.take(tok_b), o_len = s.take(len_b), o_dur = s.take(dur_b);
+  int rc = ctx->ensure_staging(s.off, s.off);
+  if (rc) return rc;
+  char* hp = (char*)ctx->hpin;
+  char* dp = (char*)ctx->dstage;
+  cudaStream_t st = ctx->own_stream;
+  memcpy(hp + o_tok, tokens, tok_b);
+  if (lengths) memcpy(hp + o_len, lengths, len_b);
+  VTTS_CUDA(cudaMemcpyAsync(dp + o_tok, hp + o_tok, tok_b, cudaMemcpyHostToDevice, st));
+  if (lengths) VTTS_CUDA(cudaMemcpyAsync(dp + o_len, hp + o_len, len_b, cudaMemcpyHostToDevice, st));
+  rc = vtts_duration_forward(ctx, (const int32_t*)(dp + o_tok), lengths ? (const int32_t*)(dp + o_len) : nullptr, B, L,
+                             (float*)(dp + o_dur), st);
+  if (rc) return rc;
+  VTTS_CUDA(cudaMemcpyAsync(hp + o_dur, dp + o_dur, dur_b, cudaMemcpyDeviceToHost, st));
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  memcpy(dur_sec, hp + o_dur, dur_b);
+  return VTTS_OK;
+}
+
+// text2mel (vietTTS/nat/text2mel.py:85-103) + mel2wave for a batch of token rows, in one call:
+//   predict_duration -> [host: silence clip, word-end zeroing, seconds -> frames, n_frames, trailing-silence trim]
+//   -> AcousticModel.inference -> Generator.  The one unavoidable host round trip is the [B,L] duration matrix:
+//   the frame count N (every later grid size) depends on it.
+int vtts_tts_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float silence_duration,
+                  int dropout_mode, uint64_t seed, int max_frames, float* dur_sec_out, int32_t* n_frames_out,
+                  int32_t* n_max_out, float* wav) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!tokens || !n_frames_out || !n_max_out || !wav || B < 1 || L < 1 || max_frames < 1)
+    return ctx->fail(VTTS_ERR_BAD_ARG, "tts_host: bad argument");
+  if (dropout_mode != VTTS_DROPOUT_OFF && dropout_mode != VTTS_DROPOUT_SEED)
+    return ctx->fail(VTTS_ERR_BAD_ARG, "tts_host: dropout_mode must be OFF or SEED (the frame count is not known to the caller)");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  std::vector<float> sec((size_t)B * L), frames((size_t)B * L);
+  int rc = vtts_predict_duration_host(ctx, tokens, lengths, B, L, sec.data());
+  if (rc) return rc;
+  std::vector<int32_t> nf_ac(B), nf_voc(B);
+  int n_max = 0;
+  for (int b = 0; b < B; ++b) {
+    const int len = lengths ? lengths[b] : L;
+    if (len < 1 || len > L) return ctx->fail(VTTS_ERR_BAD_ARG, "tts_host: lengths[%d]=%d outside [1,%d]", b, len, L);
+    double total = 0.0;
+    for (int l = 0; l < L; ++l) {
+      float d = l < len ? sec[(size_t)b * L + l] : 0.f;
+      const int tok = tokens[(size_t)b * L + l];
+      if (l < len && tok == vc::SIL_INDEX && d < silence_duration) d = silence_duration;   // text2mel.py:88-94
+      if (tok == vc::WORD_END_INDEX) d = 0.f;                                              // text2mel.py:95-97
+      sec[(size_t)b * L + l] = d;
+      const float f = (d * 16000.0f) / 256.0f;                                             // text2mel.py:78 (float32)
+      frames[(size_t)b * L + l] = f;
+      total += f;
+    }
+    const int n = (int)(float)total;                                                       // text2mel.py:79
+    int trim = 0;
+    if (tokens[(size_t)b * L + len - 1] == vc::SIL_INDEX)                                  // text2mel.py:99-102
+      trim = (int)((double)sec[(size_t)b * L + len - 1] * 16000.0 / 256.0);
+    nf_ac[b] = n;
+    nf_voc[b] = n - trim > 0 ? n - trim : 0;
+    if (n > n_max) n_max = n;
+  }
+  if (dur_sec_out) memcpy(dur_sec_out, sec.data(), sec.size() * sizeof(float));
+  memcpy(n_frames_out, nf_voc.data(), (size_t)B * sizeof(int32_t));
+  *n_max_out = n_max;
+  if (n_max < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tts_host: predicted durations sum to less than one frame");
+  if (n_max > max_frames)
+    return ctx->fail(VTTS_ERR_BAD_ARG, "tts_host: needs %d frames, caller buffer holds %d (n_max_out is set: retry with that size)", n_max, max_frames);
+  return synth_common(ctx, tokens, lengths, frames.data(), nf_ac.data(), nullptr, dropout_mode, seed, B, L, n_max, nullptr, wav,
+                      nf_voc.data());
 }
 
 int vtts_melspec_host(vtts_ctx* ctx, const float* wav, int B, int S, float* mel) {
@@ -581,7 +706,7 @@ int vtts_melspec_host(vtts_ctx* ctx, const float* wav, int B, int S, float* mel)
 int64_t vtts_launch_count(vtts_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int vtts_last_stage_ms(vtts_ctx* ctx, int stage, float* ms) {
-  if (!ctx || !ms || stage < 0 || stage > 2) return VTTS_ERR_BAD_ARG;
+  if (!ctx || !ms || stage < 0 || stage >= vtts_ctx::NSTAGE) return VTTS_ERR_BAD_ARG;
   if (!ctx->ev_valid[stage]) return ctx->fail(VTTS_ERR_BAD_ARG, "last_stage_ms: stage %d has not run", stage);
   VTTS_CUDA(cudaSetDevice(ctx->device));
   VTTS_CUDA(cudaEventSynchronize(ctx->ev1[stage]));

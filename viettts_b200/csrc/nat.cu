@@ -800,6 +800,59 @@ enum { WP_ENC = 0, WP_ENCH = 3, WP_DECH = 11, WP_POST0 = 27, WP_POST1 = 29, WP_P
 
 }  // namespace
 
+// TokenEncoder.__call__ (model.py:26-47, is_training=False): embed -> 3 x [conv k3, BN(eval), relu] -> BiLSTM.
+// The acoustic model and the duration model instantiate it with the same dimensions (config.py:11-17), so one
+// implementation serves both; only the weight pointers differ.
+struct EncWeights {
+  const float* embed;
+  const float* conv_w[3];
+  const float* conv_b[3];
+  const float* bn_off[3];
+  const float* bn_mean[3];
+  const float* bn_inv[3];
+  const float *lf_w, *lf_b, *lb_w, *lb_b;   // hk.LSTM linear of the forward / backward core, w[512][1024]
+  const float* whr;                         // [2][64][256][16] recurrent rows, per direction / CTA
+  void* const* wpk_conv;                    // 3 packed conv weights (tensor-core path)
+  void* const* wpk_hoist;                   // 8 packed tiles of the two hoisted input projections
+};
+
+static int run_token_encoder(vtts_ctx* ctx, const EncWeights& w, const int32_t* tokens, const int32_t* lengths, int B, int L,
+                             float* e0, float* e1, float* zx, float* enc, cudaStream_t st) {
+  const size_t BL = (size_t)B * L;
+  embed_kernel<<<(unsigned)((BL + 3) / 4), 256, 0, st>>>(tokens, w.embed, e0, (int)BL);
+  ctx->launches++;
+  VTTS_CUDA(cudaGetLastError());
+  ConvLaunch Lc;
+  float* cur = e0;
+  float* nxt = e1;
+  for (int i = 0; i < 3; ++i) {
+    memset(&Lc, 0, sizeof(Lc));
+    Lc.nprob = 1; Lc.Cin = 256; Lc.Cout = 256; Lc.B = B; Lc.T_rows = L; Lc.rows_out = L;
+    Lc.len = lengths; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 2;
+    Lc.p[0] = ConvProb{cur, nullptr, nullptr, w.conv_w[i], w.conv_b[i], nullptr, w.bn_mean[i], w.bn_inv[i], w.bn_off[i], nxt, 3, 1, -1, 1, 0};
+    int rc = vtts_conv_dispatch(ctx, Lc, w.wpk_conv + i, st);
+    if (rc) return rc;
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  // rows past len[b] of `cur` were never written: the scans mask them, but the hoisted GEMM reads them
+  // -> harmless garbage confined to rows that are never consumed (k=1 GEMM has no row mixing).
+  // ---- hoisted input projections of the two LSTMs: zx[dir] = x . W[0:256] + b ----
+  memset(&Lc, 0, sizeof(Lc));
+  Lc.nprob = 2; Lc.Cin = 256; Lc.Cout = 1024; Lc.B = 1; Lc.T_rows = (int)BL; Lc.rows_out = (int)BL;
+  Lc.len = nullptr; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;
+  Lc.p[0] = ConvProb{cur, nullptr, nullptr, w.lf_w, w.lf_b, nullptr, nullptr, nullptr, nullptr, zx, 1, 1, 0, 1, 0};
+  Lc.p[1] = ConvProb{cur, nullptr, nullptr, w.lb_w, w.lb_b, nullptr, nullptr, nullptr, nullptr, zx + BL * 1024, 1, 1, 0, 1, 0};
+  int rc = vtts_conv_dispatch(ctx, Lc, w.wpk_hoist, st);
+  if (rc) return rc;
+  // ---- BiLSTM scan (forward core + ResetCore'd backward core) ----
+  EncScanArgs ea;
+  ea.zx = zx; ea.whr = w.whr; ea.lengths = lengths; ea.out = enc; ea.B = B; ea.L = L;
+  void* args[] = {&ea};
+  VTTS_CUDA(cudaLaunchCooperativeKernel((void*)enc_scan_kernel, dim3(SCAN_CTAS), dim3(SCAN_THREADS), args, enc_scan_smem(), st));
+  ctx->launches++;
+  return VTTS_OK;
+}
+
 int vtts_acoustic_prepare(vtts_ctx* ctx) {
   const size_t sizes[D_COUNT] = {256, 256, 256, 512, 512, 512, 512,
                                  (size_t)2 * 64 * 256 * 16, (size_t)128 * 768 * 16, (size_t)128 * 1280 * 16,
@@ -899,40 +952,18 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   VTTS_CUDA(cudaMemsetAsync(cond, 0, BN * 512 * sizeof(float), st));
   VTTS_CUDA(cudaMemsetAsync(melpre, 0, BN * 80 * sizeof(float), st));
 
-  // ---- TokenEncoder: embed -> 3 x [conv k3, BN(eval), relu] ----
-  embed_kernel<<<(unsigned)((BL + 3) / 4), 256, 0, st>>>(tokens, T[aci::EMBED], e0, (int)BL);
-  ctx->launches++;
-  VTTS_CUDA(cudaGetLastError());
-  ConvLaunch Lc;
-  float* cur = e0;
-  float* nxt = e1;
-  for (int i = 0; i < 3; ++i) {
-    memset(&Lc, 0, sizeof(Lc));
-    Lc.nprob = 1; Lc.Cin = 256; Lc.Cout = 256; Lc.B = B; Lc.T_rows = L; Lc.rows_out = L;
-    Lc.len = lengths; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 2;
-    Lc.p[0] = ConvProb{cur, nullptr, nullptr, T[aci::ENC_CONV(i, 0)], T[aci::ENC_CONV(i, 1)], nullptr,
-                       T[aci::ENC_CONV(i, 4)], D[D_ENC_BNINV0 + i], T[aci::ENC_CONV(i, 3)], nxt, 3, 1, -1, 1, 0};
-    int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_ENC + i], st);
-    if (rc) return rc;
-    float* tmp = cur; cur = nxt; nxt = tmp;
-  }
-  // rows past len[b] of `cur` were never written: the scans mask them, but the hoisted GEMM reads them
-  // -> harmless garbage confined to rows that are never consumed (k=1 GEMM has no row mixing).
-  // ---- hoisted input projections of the two encoder LSTMs: zx[dir] = x . W[0:256] + b ----
-  memset(&Lc, 0, sizeof(Lc));
-  Lc.nprob = 2; Lc.Cin = 256; Lc.Cout = 1024; Lc.B = 1; Lc.T_rows = (int)BL; Lc.rows_out = (int)BL;
-  Lc.len = nullptr; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;
-  Lc.p[0] = ConvProb{cur, nullptr, nullptr, T[aci::ENC_LSTM_F_W], T[aci::ENC_LSTM_F_B], nullptr, nullptr, nullptr, nullptr, zx, 1, 1, 0, 1, 0};
-  Lc.p[1] = ConvProb{cur, nullptr, nullptr, T[aci::ENC_LSTM_B_W], T[aci::ENC_LSTM_B_B], nullptr, nullptr, nullptr, nullptr, zx + BL * 1024, 1, 1, 0, 1, 0};
-  int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_ENCH], st);
-  if (rc) return rc;
-  // ---- BiLSTM scan ----
+  // ---- TokenEncoder (shared with the duration model, run_token_encoder above) ----
   {
-    EncScanArgs ea;
-    ea.zx = zx; ea.whr = D[D_ENC_WHR]; ea.lengths = lengths; ea.out = enc; ea.B = B; ea.L = L;
-    void* args[] = {&ea};
-    VTTS_CUDA(cudaLaunchCooperativeKernel((void*)enc_scan_kernel, dim3(SCAN_CTAS), dim3(SCAN_THREADS), args, enc_scan_smem(), st));
-    ctx->launches++;
+    EncWeights ew;
+    ew.embed = T[aci::EMBED];
+    for (int i = 0; i < 3; ++i) {
+      ew.conv_w[i] = T[aci::ENC_CONV(i, 0)]; ew.conv_b[i] = T[aci::ENC_CONV(i, 1)];
+      ew.bn_off[i] = T[aci::ENC_CONV(i, 3)]; ew.bn_mean[i] = T[aci::ENC_CONV(i, 4)]; ew.bn_inv[i] = D[D_ENC_BNINV0 + i];
+    }
+    ew.lf_w = T[aci::ENC_LSTM_F_W]; ew.lf_b = T[aci::ENC_LSTM_F_B]; ew.lb_w = T[aci::ENC_LSTM_B_W]; ew.lb_b = T[aci::ENC_LSTM_B_B];
+    ew.whr = D[D_ENC_WHR]; ew.wpk_conv = &ctx->ac_wpk_t[WP_ENC]; ew.wpk_hoist = &ctx->ac_wpk_t[WP_ENCH];
+    int rc = run_token_encoder(ctx, ew, tokens, lengths, B, L, e0, e1, zx, enc, st);
+    if (rc) return rc;
   }
   // ---- Gaussian upsampling ----
   {
@@ -945,12 +976,13 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     VTTS_CUDA(cudaGetLastError());
   }
   // ---- hoisted cond projections of the decoder LSTMs ----
+  ConvLaunch Lc;
   memset(&Lc, 0, sizeof(Lc));
   Lc.nprob = 2; Lc.Cin = 512; Lc.Cout = 2048; Lc.B = 1; Lc.T_rows = (int)BN; Lc.rows_out = (int)BN;
   Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0; Lc.len_mul = 1;
   Lc.p[0] = ConvProb{cond, nullptr, nullptr, T[aci::DEC_L0_W], T[aci::DEC_L0_B], nullptr, nullptr, nullptr, nullptr, zc0, 1, 1, 0, 1, 0};
   Lc.p[1] = ConvProb{cond, nullptr, nullptr, T[aci::DEC_L1_W], T[aci::DEC_L1_B], nullptr, nullptr, nullptr, nullptr, zc1, 1, 1, 0, 1, 0};
-  rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_DECH], st);
+  int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_DECH], st);
   if (rc) return rc;
   // ---- autoregressive scan: launches of up to 32 rows (rows are independent) ----
   for (int b0 = 0; b0 < B; b0 += DEC_XR) {
@@ -989,5 +1021,140 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     pout = (pout == q0) ? q1 : q0;
     cin = cout;
   }
+  return VTTS_OK;
+}
+
+// =====================================================================================================
+// DurationModel (vietTTS/nat/model.py:49-70): TokenEncoder -> Linear(512->256) -> gelu -> Linear(256->1) -> softplus.
+// The encoder is run_token_encoder above with the duration checkpoint's weights; the first Linear is a k=1
+// contraction through the shared conv dispatch; the head below finishes gelu / dot / softplus per token.
+// =====================================================================================================
+namespace {
+
+// jax.nn.gelu default (approximate=True): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+// jax.nn.softplus = logaddexp(x, 0)
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+// one warp per token: y [BL][256] (pre-activation of the first Linear, bias included) -> dur[BL] seconds
+__global__ void __launch_bounds__(256) duration_head_kernel(const float* __restrict__ y, const float* __restrict__ w2,
+                                                            const float* __restrict__ b2, const int32_t* __restrict__ lengths,
+                                                            int B, int L, float* __restrict__ dur) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * 8 + warp;
+  if (tok >= B * L) return;
+  const int b = tok / L, l = tok - b * L;
+  if (lengths && l >= lengths[b]) {
+    if (lane == 0) dur[tok] = 0.f;
+    return;
+  }
+  const float* yr = y + (size_t)tok * 256 + lane * 8;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(yr)), a1 = __ldg(reinterpret_cast<const float4*>(yr + 4));
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(w2 + lane * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w2 + lane * 8 + 4));
+  float s = gelu_tanh(a0.x) * w0.x;
+  s = fmaf(gelu_tanh(a0.y), w0.y, s);
+  s = fmaf(gelu_tanh(a0.z), w0.z, s);
+  s = fmaf(gelu_tanh(a0.w), w0.w, s);
+  s = fmaf(gelu_tanh(a1.x), w1.x, s);
+  s = fmaf(gelu_tanh(a1.y), w1.y, s);
+  s = fmaf(gelu_tanh(a1.z), w1.z, s);
+  s = fmaf(gelu_tanh(a1.w), w1.w, s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dur[tok] = softplus(s + __ldg(b2));
+}
+
+enum { DU_BNINV0 = 0, DU_BNINV1, DU_BNINV2, DU_WHR, DU_COUNT };
+enum { DWP_ENC = 0, DWP_ENCH = 3, DWP_FC1 = 11, DWP_COUNT = 12 };
+
+}  // namespace
+
+int vtts_duration_prepare(vtts_ctx* ctx) {
+  const size_t sizes[DU_COUNT] = {256, 256, 256, (size_t)2 * 64 * 256 * 16};
+  size_t total = 0;
+  std::vector<size_t> offs(DU_COUNT);
+  for (int i = 0; i < DU_COUNT; ++i) {
+    offs[i] = total;
+    total += (sizes[i] + 63) & ~size_t(63);
+  }
+  if (ctx->du_derived) cudaFree(ctx->du_derived);
+  VTTS_CUDA(cudaMalloc(&ctx->du_derived, total * sizeof(float)));
+  ctx->du_d.resize(DU_COUNT);
+  for (int i = 0; i < DU_COUNT; ++i) ctx->du_d[i] = ctx->du_derived + offs[i];
+  auto& T = ctx->du_t;
+  for (int i = 0; i < 3; ++i) bn_inv_kernel<<<1, 256>>>(T[aci::ENC_CONV(i, 2)], T[aci::ENC_CONV(i, 5)], ctx->du_d[DU_BNINV0 + i], 256);
+  repack_cols_kernel<<<256, 256>>>(T[aci::ENC_LSTM_F_W], 1024, 256, 256, ctx->du_d[DU_WHR], 64, 16, UPC, 256);
+  repack_cols_kernel<<<256, 256>>>(T[aci::ENC_LSTM_B_W], 1024, 256, 256, ctx->du_d[DU_WHR] + (size_t)64 * 256 * 16, 64, 16, UPC, 256);
+  VTTS_CUDA(cudaGetLastError());
+  {
+    const size_t bytes = 3 * vtts_tc_conv_packed_bytes(3, 256, 256) + 2 * vtts_tc_conv_packed_bytes(1, 256, 1024) +
+                         vtts_tc_conv_packed_bytes(1, 512, 256);
+    if (ctx->du_wpk) cudaFree(ctx->du_wpk);
+    VTTS_CUDA(cudaMalloc(&ctx->du_wpk, bytes));
+    char* cur = (char*)ctx->du_wpk;
+    ctx->du_wpk_t.clear();
+    int rc = 0;
+    for (int i = 0; i < 3 && !rc; ++i) rc = vtts_tc_pack_conv(ctx, T[aci::ENC_CONV(i, 0)], 3, 256, 256, cur, ctx->du_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::ENC_LSTM_F_W], 1, 256, 1024, cur, ctx->du_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::ENC_LSTM_B_W], 1, 256, 1024, cur, ctx->du_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[dui::FC1_W], 1, 512, 256, cur, ctx->du_wpk_t);
+    if (rc) return rc;
+    if ((int)ctx->du_wpk_t.size() != DWP_COUNT || (size_t)(cur - (char*)ctx->du_wpk) > bytes)
+      return ctx->fail(VTTS_ERR_BAD_ARG, "duration: packed weight table has %d entries", (int)ctx->du_wpk_t.size());
+  }
+  VTTS_CUDA(cudaDeviceSynchronize());
+  VTTS_CUDA(cudaFuncSetAttribute(enc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_scan_smem()));
+  return VTTS_OK;
+}
+
+int vtts_duration_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float* dur_sec,
+                      cudaStream_t st, void* ws_base, size_t ws_cap, size_t* ws_need) {
+  const bool measure = ws_need != nullptr;
+  if (!measure) {
+    if (!ctx->du_loaded) return ctx->fail(VTTS_ERR_NOT_LOADED, "duration weights not loaded");
+    if (B < 1 || L < 1 || B > MAX_ROWS)
+      return ctx->fail(VTTS_ERR_BAD_ARG, "duration: B=%d L=%d (1 <= B <= %d rows per call; the host layer chunks larger batches)", B, L, MAX_ROWS);
+    if (ctx->sm_count < SCAN_CTAS) return ctx->fail(VTTS_ERR_NO_DEVICE, "scan kernels need %d SMs, device has %d", SCAN_CTAS, ctx->sm_count);
+  }
+  Arena ar(ws_base, ws_cap, measure);
+  const size_t BL = (size_t)B * L;
+  float* e0 = ar.take<float>(BL * 256);
+  float* e1 = ar.take<float>(BL * 256);
+  float* zx = ar.take<float>(2 * BL * 1024);
+  float* enc = ar.take<float>(BL * 512);
+  float* y = ar.take<float>(BL * 256);
+  if (measure) {
+    *ws_need = ar.off + 256;
+    return VTTS_OK;
+  }
+  auto& T = ctx->du_t;
+  auto& D = ctx->du_d;
+  EncWeights ew;
+  ew.embed = T[aci::EMBED];
+  for (int i = 0; i < 3; ++i) {
+    ew.conv_w[i] = T[aci::ENC_CONV(i, 0)]; ew.conv_b[i] = T[aci::ENC_CONV(i, 1)];
+    ew.bn_off[i] = T[aci::ENC_CONV(i, 3)]; ew.bn_mean[i] = T[aci::ENC_CONV(i, 4)]; ew.bn_inv[i] = D[DU_BNINV0 + i];
+  }
+  ew.lf_w = T[aci::ENC_LSTM_F_W]; ew.lf_b = T[aci::ENC_LSTM_F_B]; ew.lb_w = T[aci::ENC_LSTM_B_W]; ew.lb_b = T[aci::ENC_LSTM_B_B];
+  ew.whr = D[DU_WHR]; ew.wpk_conv = &ctx->du_wpk_t[DWP_ENC]; ew.wpk_hoist = &ctx->du_wpk_t[DWP_ENCH];
+  // padded encoder rows are never written by the scan: clear them so the projection reads zeros, not stale workspace
+  VTTS_CUDA(cudaMemsetAsync(enc, 0, BL * 512 * sizeof(float), st));
+  int rc = run_token_encoder(ctx, ew, tokens, lengths, B, L, e0, e1, zx, enc, st);
+  if (rc) return rc;
+  ctx->tap_enc = enc; ctx->tap_enc_n = BL * 512;
+  // ---- projection head ----
+  ConvLaunch Lc;
+  memset(&Lc, 0, sizeof(Lc));
+  Lc.nprob = 1; Lc.Cin = 512; Lc.Cout = 256; Lc.B = 1; Lc.T_rows = (int)BL; Lc.rows_out = (int)BL;
+  Lc.len = nullptr; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;
+  Lc.p[0] = ConvProb{enc, nullptr, nullptr, T[dui::FC1_W], T[dui::FC1_B], nullptr, nullptr, nullptr, nullptr, y, 1, 1, 0, 1, 0};
+  rc = vtts_conv_dispatch(ctx, Lc, &ctx->du_wpk_t[DWP_FC1], st);
+  if (rc) return rc;
+  duration_head_kernel<<<(unsigned)((BL + 7) / 8), 256, 0, st>>>(y, T[dui::FC2_W], T[dui::FC2_B], lengths, B, L, dur_sec);
+  ctx->launches++;
+  VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
 }

@@ -21,6 +21,8 @@ constexpr int DEC_H = 512;        // acoustic_decoder_dim
 constexpr int PRENET = 256;
 constexpr int POSTNET = 512;
 constexpr int VOCAB = 256;
+constexpr int SIL_INDEX = 0;      // nat/config.py:26 special_phonemes.index("sil")
+constexpr int WORD_END_INDEX = 3; // nat/config.py:28 special_phonemes.index(" ")
 constexpr int HG_C0 = 512;        // upsample_initial_channel
 constexpr int HG_NSTAGE = 4;
 __host__ __device__ constexpr int hg_rate(int i) { return i < 2 ? 8 : 2; }
@@ -164,6 +166,14 @@ struct vtts_ctx {
   std::vector<float*> ac_d;
   bool ac_loaded = false;
 
+  float* du_blob = nullptr;     // duration model (TokenEncoder + projection head), same layout rules as ac_*
+  std::vector<float*> du_t;
+  void* du_wpk = nullptr;
+  std::vector<void*> du_wpk_t;
+  float* du_derived = nullptr;
+  std::vector<float*> du_d;
+  bool du_loaded = false;
+
   // mel filterbank + fft tables
   float* mel_fb = nullptr;      // dense [80][513]
   int* mel_lo = nullptr;        // [80] first non-zero bin
@@ -186,10 +196,11 @@ struct vtts_ctx {
   float* tap_cond = nullptr; int64_t tap_cond_n = 0;
   float* tap_melpre = nullptr; int64_t tap_melpre_n = 0;
 
-  cudaEvent_t ev0[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev1[3] = {nullptr, nullptr, nullptr};
-  cudaStream_t ev_stream[3] = {nullptr, nullptr, nullptr};
-  bool ev_valid[3] = {false, false, false};
+  static constexpr int NSTAGE = 4;   // 0 hifigan, 1 acoustic, 2 melspec, 3 duration
+  cudaEvent_t ev0[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev1[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t ev_stream[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid[NSTAGE] = {false, false, false, false};
 
   int fail(int code, const char* fmt, ...);
   int ensure_ws(size_t bytes);
@@ -240,12 +251,17 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
                       float* mel, cudaStream_t st, void* ws_base, size_t ws_cap, size_t* ws_need);
 // melspec.cu
 int vtts_melspec_prepare(vtts_ctx* ctx);
+int vtts_duration_prepare(vtts_ctx* ctx);
+// DurationModel.__call__ (model.py:64-70); dur_sec [B][L] seconds, 0 past lengths[b]
+int vtts_duration_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float* dur_sec,
+                      cudaStream_t st, void* ws_base, size_t ws_cap, size_t* ws_need);
 int vtts_melspec_run(vtts_ctx* ctx, const float* wav, int B, int S, float* mel, cudaStream_t st);
 
 // canonical blob layouts (weights.cu)
 struct TensorSpec { const char* name; int64_t n; };
 const std::vector<TensorSpec>& vtts_hifigan_specs();
 const std::vector<TensorSpec>& vtts_acoustic_specs();
+const std::vector<TensorSpec>& vtts_duration_specs();
 
 // indices into ctx->hg_t  (canonical order: pre, ups 0..3, resblocks 0..11 x (c1_0,c1_1,c1_2,c2_0,c2_1,c2_2), post)
 namespace hgi {
@@ -271,3 +287,10 @@ constexpr int PROJ_W = 27, PROJ_B = 28, PRE1_W = 29, PRE2_W = 30;
 __host__ __device__ constexpr int POST_CONV(int i, int f) { return 31 + i * 6 + f; }
 constexpr int COUNT = 31 + 4 * 6 + 2;
 }  // namespace aci
+
+// indices into ctx->du_t (duration model): the TokenEncoder block has the acoustic model's layout (aci::EMBED ..
+// aci::ENC_LSTM_B_B), followed by the projection head hk.Sequential([Linear(256), gelu, Linear(1)]) (model.py:60-62)
+namespace dui {
+constexpr int FC1_W = 23, FC1_B = 24, FC2_W = 25, FC2_B = 26;
+constexpr int COUNT = 27;
+}  // namespace dui

@@ -46,6 +46,7 @@ class Engine:
         self.h = h
         self._hifigan_key = None
         self._acoustic_key = None
+        self._duration_key = None
         self._mel_loaded = False
 
     def close(self):
@@ -132,6 +133,15 @@ class Engine:
         self._ck(self.lib.vtts_load_acoustic(self.h, _ptr(blob), n))
         self._acoustic_key = key if key is not None else object()
 
+    def load_duration(self, ckpt, key=None):
+        """ckpt: the duration checkpoint dict (params/aux), a packed numpy blob, or a torch CUDA tensor."""
+        blob = weights.pack_duration(ckpt) if isinstance(ckpt, dict) else ckpt
+        n = int(blob.size if isinstance(blob, np.ndarray) else blob.numel())
+        if isinstance(blob, np.ndarray):
+            blob = _np(blob, np.float32)
+        self._ck(self.lib.vtts_load_duration(self.h, _ptr(blob), n))
+        self._duration_key = key if key is not None else object()
+
     def load_mel_filterbank(self, fb=None):
         fb = _np(weights.mel_filterbank() if fb is None else fb, np.float32, (config.MEL_DIM, config.N_FFT // 2 + 1), "filterbank")
         self._ck(self.lib.vtts_load_mel_filterbank(self.h, _ptr(fb), fb.shape[0], fb.shape[1]))
@@ -195,6 +205,24 @@ class Engine:
             mel[sl] = out
         return mel
 
+    def predict_duration(self, tokens, lengths=None) -> np.ndarray:
+        """DurationModel.__call__ (nat/model.py:64-70) for a (ragged) batch: tokens int [B,L] -> predicted
+        durations in SECONDS f32 [B,L] (0 past lengths[b]); row b equals the reference run on row b alone."""
+        tokens = _np(tokens, np.int32)
+        if tokens.ndim != 2:
+            raise ValueError("tokens must be [B,L]")
+        B, L = tokens.shape
+        lens = None if lengths is None else _np(lengths, np.int32, (B,), "lengths")
+        out = np.empty((B, L), np.float32)
+        for b0 in range(0, B, MAX_ACOUSTIC_ROWS):
+            b1 = min(B, b0 + MAX_ACOUSTIC_ROWS)
+            o = np.empty((b1 - b0, L), np.float32)
+            self._ck(self.lib.vtts_predict_duration_host(
+                self.h, _ptr(np.ascontiguousarray(tokens[b0:b1])), _ptr(None if lens is None else np.ascontiguousarray(lens[b0:b1])),
+                b1 - b0, L, _ptr(o)))
+            out[b0:b1] = o
+        return out
+
     @staticmethod
     def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
         """numpy array backed by page-locked host memory.  Passed as `out=` to synthesize / mel2wave the
@@ -233,6 +261,35 @@ class Engine:
             if return_mel:
                 mel[sl] = m
         return (wav, mel) if return_mel else wav
+
+    def tts(self, tokens, lengths=None, silence_duration=-1.0, seed=None, max_frames=None):
+        """Token rows -> waveforms in ONE library call (vtts_tts_host): duration model, the duration fix-ups of
+        text2mel.py:88-97, acoustic model, trailing-silence trim (:99-102) and generator, the mel never leaving
+        the device.  tokens int [B,L] (rows padded to L), lengths int [B].  Returns (list of f32 waveforms,
+        durations_sec f32 [B,L])."""
+        tokens = _np(tokens, np.int32)
+        if tokens.ndim != 2:
+            raise ValueError("tokens must be [B,L]")
+        B, L = tokens.shape
+        if B > MAX_ACOUSTIC_ROWS:
+            raise ValueError(f"tts: at most {MAX_ACOUSTIC_ROWS} rows per call")
+        lens = None if lengths is None else _np(lengths, np.int32, (B,), "lengths")
+        dur = np.empty((B, L), np.float32)
+        nf = np.zeros(B, np.int32)
+        nmax = C.c_int32(0)
+        cap = int(max_frames) if max_frames else max(16, int(L * 0.12 * config.SAMPLE_RATE / config.HOP))
+        mode = DROPOUT_SEED if seed is not None else DROPOUT_OFF
+        for _ in range(2):
+            wav = np.empty(B * cap * config.HOP, np.float32)
+            rc = self.lib.vtts_tts_host(self.h, _ptr(tokens), _ptr(lens), B, L, float(silence_duration), mode, int(seed or 0),
+                                        cap, _ptr(dur), _ptr(nf), C.byref(nmax), _ptr(wav))
+            if rc == 0 or not (0 < cap < nmax.value):
+                break
+            cap = int(nmax.value)       # buffer too small: the call reported the size it needs
+        self._ck(rc)
+        n = int(nmax.value)
+        wav = wav[: B * n * config.HOP].reshape(B, n * config.HOP)
+        return [wav[b, : int(nf[b]) * config.HOP].copy() for b in range(B)], dur
 
     def synthesize_many(self, utterances, seed=None, masks=None, max_pad_frac=0.08, max_rows=32):
         """Mixed-length workload (BASELINE configs[4]): `utterances` is a list of (tokens list[int],
@@ -298,6 +355,16 @@ class Engine:
         st = torch.cuda.current_stream(tokens_t.device).cuda_stream if stream is None else stream
         self._ck(self.lib.vtts_acoustic_forward(self.h, _ptr(tokens_t), _ptr(lengths_t), _ptr(dur_t), _ptr(n_frames_t),
                                                 _ptr(masks_t), mode, int(seed or 0), B, L, int(N), _ptr(out), st))
+        return out
+
+    def duration_forward(self, tokens_t, lengths_t=None, out=None, stream=None):
+        import torch
+        assert tokens_t.is_cuda and tokens_t.dtype == torch.int32 and tokens_t.is_contiguous()
+        B, L = tokens_t.shape
+        if out is None:
+            out = torch.empty((B, L), dtype=torch.float32, device=tokens_t.device)
+        st = torch.cuda.current_stream(tokens_t.device).cuda_stream if stream is None else stream
+        self._ck(self.lib.vtts_duration_forward(self.h, _ptr(tokens_t), _ptr(lengths_t), B, L, _ptr(out), st))
         return out
 
     def melspec_forward(self, wav_t, out=None, stream=None):

@@ -117,6 +117,27 @@ def acoustic_ckpt(seed: int = 1234) -> dict:
     return dict(step=0, params=P, aux=S, rng=np.array([0, 42], np.uint32), optim_state=None)
 
 
+def duration_ckpt(seed: int = 1234) -> dict:
+    """Checkpoint dict with the keys predict_duration reads (text2mel.py:27-34): params / aux / rng.
+    DurationModel (model.py:49-70): TokenEncoder(vocab, 256) + Sequential([Linear(256), gelu, Linear(1)])."""
+    rng = np.random.default_rng(seed + 2)
+    P, S = {}, {}
+    M = "duration_model/~/"
+    T = M + "token_encoder/~/"
+    D = C.DURATION_LSTM_DIM
+    P[T + "embed"] = dict(embeddings=_normal(rng, (C.VOCAB_SIZE, D), 1.0))
+    for i in range(3):
+        sfx = "" if i == 0 else f"_{i}"
+        P[T + "conv1_d" + sfx] = dict(w=_normal(rng, (3, D, D), 1.4 / np.sqrt(3 * D)), b=_normal(rng, (D,), 0.05))
+        _bn(rng, T + "batch_norm" + sfx, D, P, S)
+    for name in ("lstm", "lstm_1"):
+        P[T + name + "/linear"] = dict(w=_normal(rng, (2 * D, 4 * D), 1.0 / np.sqrt(2 * D)), b=_normal(rng, (4 * D,), 0.05))
+    P[M + "linear"] = dict(w=_normal(rng, (2 * D, D), 2.0 / np.sqrt(2 * D)), b=_normal(rng, (D,), 0.1))
+    # head bias -2.5: softplus(-2.5) = 0.079 s, a plausible phoneme duration; the weights spread it over ~0.02..0.3 s
+    P[M + "linear_1"] = dict(w=_normal(rng, (D, 1), 3.0 / np.sqrt(D)), b=np.array([-2.5], np.float32))
+    return dict(step=0, params=P, aux=S, rng=np.array([0, 43], np.uint32), optim_state=None)
+
+
 # ---------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md §8d: C1..C5)
 # ---------------------------------------------------------------------------

@@ -163,6 +163,36 @@ def pack_acoustic(ckpt: dict) -> np.ndarray:
     return np.concatenate(parts)
 
 
+def pack_duration(ckpt: dict) -> np.ndarray:
+    """duration_latest_ckpt.pickle contents {"params","aux",...} (text2mel.py:27-34) -> float32 blob in
+    vtts_duration_specs order: the TokenEncoder tensors (same order as in the acoustic blob), then the
+    projection head Linear(512->256), Linear(256->1) (model.py:60-62)."""
+    P, S = ckpt["params"], ckpt["aux"]
+    M = "duration_model/~/"
+    T = M + "token_encoder/~/"
+    D = C.DURATION_LSTM_DIM
+    parts = [_arr(_get(P, T + "embed")["embeddings"], (C.VOCAB_SIZE, D), "embed")]
+    for i in range(3):
+        sfx = "" if i == 0 else f"_{i}"
+        m = _get(P, T + "conv1_d" + sfx)
+        parts += [_arr(m["w"], (3, D, D), f"enc.conv{i}.w"), _arr(m["b"], (D,), f"enc.conv{i}.b")]
+        bn = _get(P, T + "batch_norm" + sfx)
+        parts += [
+            _arr(bn["scale"], (D,), f"enc.bn{i}.scale"),
+            _arr(bn["offset"], (D,), f"enc.bn{i}.offset"),
+            _arr(_get(S, T + "batch_norm" + sfx + "/~/mean_ema")["average"], (D,), f"enc.bn{i}.mean"),
+            _arr(_get(S, T + "batch_norm" + sfx + "/~/var_ema")["average"], (D,), f"enc.bn{i}.var"),
+        ]
+    for name in ("lstm", "lstm_1"):
+        m = _get(P, T + name + "/linear")
+        parts += [_arr(m["w"], (2 * D, 4 * D), f"enc.{name}.w"), _arr(m["b"], (4 * D,), f"enc.{name}.b")]
+    m = _get(P, M + "linear")
+    parts += [_arr(m["w"], (2 * D, D), "proj.fc1.w"), _arr(m["b"], (D,), "proj.fc1.b")]
+    m = _get(P, M + "linear_1")
+    parts += [_arr(m["w"], (D, 1), "proj.fc2.w"), _arr(m["b"], (1,), "proj.fc2.b")]
+    return np.concatenate(parts)
+
+
 # ---------------------------------------------------------------------------
 # librosa-compatible mel filterbank (MelFilter.__init__, dsp.py:107-113)
 # ---------------------------------------------------------------------------
