@@ -142,6 +142,33 @@ def main():
     assert worst < 1e-5
 
     out_dir = Path(__file__).resolve().parent
+    # --- step 3b: converter fixture with a NON-trivial weight norm (random g), a few small tensors only ---
+    rng = np.random.default_rng(11)
+    sd_wn2 = {k: (v * torch.from_numpy(rng.uniform(0.5, 1.5, size=tuple(v.shape)).astype(np.float32)) if k.endswith("weight_g") else v)
+              for k, v in sd_wn.items()}
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "g_synth2")
+        torch.save({"generator": sd_wn2}, ck)
+        cwd = os.getcwd()
+        os.chdir(td)
+        try:
+            cv.convert_to_haiku(types.SimpleNamespace(checkpoint_file=ck), h, torch.device("cpu"))
+            with open(Path(td) / "assets/infore/hifigan/hk_hifi.pickle", "rb") as f:
+                hk_ref2 = pickle.load(f)
+        finally:
+            os.chdir(cwd)
+    fx = {}
+    for tname, hname in (("ups.3", "generator/~/ups_3"), ("ups.2", "generator/~/ups_2"),
+                         ("resblocks.9.convs1.0", "generator/~/res_block1_9/~/convs1_0"),
+                         ("resblocks.11.convs2.2", "generator/~/res_block1_11/~/convs2_2"),
+                         ("conv_post", "generator/~/conv1_d_1")):
+        for suffix in ("weight_g", "weight_v", "bias"):
+            fx[f"torch/{tname}.{suffix}"] = sd_wn2[f"{tname}.{suffix}"].numpy()
+        fx[f"haiku/{hname}/w"] = np.ascontiguousarray(hk_ref2[hname]["w"])
+        fx[f"haiku/{hname}/b"] = hk_ref2[hname]["b"]
+    np.savez_compressed(out_dir / "hifigan_converter_ref.npz", **fx)
+    print("converter fixture:", len(fx), "arrays")
+
     for tag, (B, T, seed) in {"small": (2, 12, 7), "t32": (1, 32, 0)}.items():
         mel = synthetic.mel_input(seed, B, T)
         acts = {}

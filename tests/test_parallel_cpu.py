@@ -54,10 +54,14 @@ def _worker(rank, world, port, q):
         hp = synthetic.hifigan_params(1234) if rank == 0 else None
         blob = weights.pack_hifigan(hp) if rank == 0 else 13_926_017
         t = parallel.broadcast_blob(blob, torch.device("cpu"), src=0)
+        # the duration model's blob: rank 1 only knows its size, from the library
+        from viettts_b200 import _lib
+        dblob = weights.pack_duration(synthetic.duration_ckpt(1234)) if rank == 0 else int(_lib.load().vtts_duration_blob_floats())
+        td = parallel.broadcast_blob(dblob, torch.device("cpu"), src=0)
         # every rank shards the same global work list identically and takes its own slice
         nf = np.random.default_rng(5).integers(156, 938, size=64)
         mine = parallel.lpt_shard(nf, world)[rank]
-        q.put((rank, float(t.double().sum()), int(t.numel()), sorted(mine)))
+        q.put((rank, float(t.double().sum()) + float(td.double().sum()) * 1e-3, int(t.numel()), sorted(mine)))
     finally:
         dist.destroy_process_group()
 

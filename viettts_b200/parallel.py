@@ -62,9 +62,11 @@ def broadcast_blob(blob_np, device, src: int = 0, group=None):
     return t
 
 
-def load_weights_distributed(engine, hifigan_params=None, acoustic_ckpt=None, device=None, src: int = 0, group=None):
+def load_weights_distributed(engine, hifigan_params=None, acoustic_ckpt=None, device=None, src: int = 0, group=None,
+                             duration_ckpt=None, with_duration: bool = False):
     """Rank `src` packs the Haiku-layout checkpoints; every rank receives the packed
-    blobs by one broadcast each and loads them from DEVICE memory (no host round trip)."""
+    blobs by one broadcast each and loads them from DEVICE memory (no host round trip).
+    `with_duration` (same value on every rank) adds the duration model's blob (55.7 + 50.1 + 7.4 MB)."""
     import torch
     import torch.distributed as dist
 
@@ -80,4 +82,11 @@ def load_weights_distributed(engine, hifigan_params=None, acoustic_ckpt=None, de
     torch.cuda.synchronize(device)
     engine.load_hifigan(ht)
     engine.load_acoustic(at)
-    return ht.numel() * 4 + at.numel() * 4
+    total = ht.numel() * 4 + at.numel() * 4
+    if with_duration or duration_ckpt is not None:
+        db = weights.pack_duration(duration_ckpt) if rank == src else int(lib.vtts_duration_blob_floats())
+        dt = broadcast_blob(db, device, src, group)
+        torch.cuda.synchronize(device)
+        engine.load_duration(dt)
+        total += dt.numel() * 4
+    return total
