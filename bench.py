@@ -339,6 +339,37 @@ def run_ours(args):
                         note="FFT-1024 in shared memory (5 radix-4 passes, 2 frames per complex FFT); latency/compute bound, not yet at the HBM roofline")
         del wav_m, mel_m
 
+    # ---- callers of the path: duration model + one-call token->wav, chunked vocoding latency ----
+    callers = None
+    if rank == 0:
+        eng.load_duration(synthetic.duration_ckpt(1234))
+        for _ in range(2):
+            waves, _ = eng.tts(tokens, silence_duration=0.05, seed=seed)
+        t0 = time.perf_counter()
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
+            waves, _ = eng.tts(tokens, silence_duration=0.05, seed=seed)
+        dt_tts = (time.perf_counter() - t0) / reps
+        tts_samples = int(sum(w.size for w in waves))
+        dur_ms = eng.last_stage_ms(3)
+        mel1 = synthetic.mel_input(3, 1, N)
+        for _ in range(2):
+            next(eng.mel2wave_stream(mel1, chunk_frames=32))
+        t0 = time.perf_counter()
+        for _ in range(10):
+            next(eng.mel2wave_stream(mel1, chunk_frames=32))
+        first_ms = (time.perf_counter() - t0) / 10 * 1e3
+        t0 = time.perf_counter()
+        n_stream = sum(p.size for p in eng.mel2wave_stream(mel1, chunk_frames=32))
+        all_ms = (time.perf_counter() - t0) * 1e3
+        callers = dict(
+            text_to_wav=dict(api="vtts_tts_host (duration model -> duration fix-ups -> acoustic -> trailing-silence trim -> generator), host buffers",
+                             batch=B, samples_per_s=tts_samples / dt_tts, ms_per_call=dt_tts * 1e3, samples_per_call=tts_samples,
+                             duration_model_ms=dur_ms),
+            streaming_vocoder=dict(api="Engine.mel2wave_stream, B=1, 32-frame chunks + 16-frame recomputed halo, host buffers",
+                                   first_chunk_ms=first_ms, audio_ms_per_chunk=32 * C.HOP / C.SAMPLE_RATE * 1e3,
+                                   whole_utterance_ms=all_ms, samples=n_stream))
+
     if rank == 0:
         pk = peaks()
         frames = int(nfs.sum())
@@ -376,7 +407,7 @@ def run_ours(args):
                           peak_source=pk["source"] + ", sustained bf16 dense",
                           note=("algorithmic fp32 FLOPs; the bf16x3 path issues 3 bf16 MMAs per algorithmic product, so 1/3 of the bf16 peak is its ceiling"
                                 if args.precision != "fp32" else "strict-fp32 path runs on the FP32 FMA pipe (nominal 74 TFLOP/s)")),
-            clocks=clocks, weights=dict(bytes=wbytes, broadcast_s=t_w), melspec=mel_info,
+            clocks=clocks, weights=dict(bytes=wbytes, broadcast_s=t_w), melspec=mel_info, callers=callers,
         )
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(synthetic.hifigan_params(1234), synthetic.acoustic_ckpt(1234), args.phonemes, args.seconds)

@@ -161,6 +161,32 @@ class Engine:
         self._ck(self.lib.vtts_mel2wave_host(self.h, _ptr(mel), _ptr(nf), B, T, _ptr(wav)))
         return wav
 
+    # receptive field of the generator in mel frames, one side: conv_pre 3 + ups_0 1 + stage-0 ResBlocks 60/8 +
+    # stage 1 60/64 + stage 2 60/128 + stage 3 60/256 + ups/conv_post crumbs = 13.3 (hifigan/model.py:44-51,109-125)
+    STREAM_HALO = 16
+
+    def mel2wave_stream(self, mel, chunk_frames: int = 32, halo: int | None = None):
+        """Chunked vocoding of ONE utterance for low first-audio latency: yields the waveform
+        in pieces of `chunk_frames` mel frames.  Each piece is computed from its frames plus `halo` frames of
+        context on both sides (recomputed, not carried), so the concatenation equals `mel2wave(mel)` exactly:
+        every output sample sees its full receptive field, and samples inside the halo are discarded."""
+        mel = _np(mel, np.float32)
+        if mel.ndim == 3:
+            if mel.shape[0] != 1:
+                raise ValueError("mel2wave_stream takes one utterance ([T,80] or [1,T,80])")
+            mel = mel[0]
+        if mel.ndim != 2 or mel.shape[1] != config.MEL_DIM:
+            raise ValueError(f"mel must be [T,{config.MEL_DIM}], got {mel.shape}")
+        halo = self.STREAM_HALO if halo is None else int(halo)
+        if chunk_frames < 1 or halo < 0:
+            raise ValueError("chunk_frames >= 1 and halo >= 0 required")
+        T = mel.shape[0]
+        for t0 in range(0, T, chunk_frames):
+            t1 = min(T, t0 + chunk_frames)
+            a, b = max(0, t0 - halo), min(T, t1 + halo)
+            wav = self.mel2wave(mel[None, a:b])[0]
+            yield wav[(t0 - a) * config.HOP: (t1 - a) * config.HOP]
+
     def _acoustic_args(self, tokens, dur_frames, lengths, n_frames, masks, seed):
         tokens = _np(tokens, np.int32)
         if tokens.ndim != 2:
