@@ -12,6 +12,7 @@
  *   vietTTS/nat/text2mel.py:62-71         pickle.load(acoustic)    -> vtts_load_acoustic
  *   vietTTS/nat/text2mel.py:22-34         predict_duration(tokens) -> vtts_predict_duration_host / vtts_duration_forward
  *   vietTTS/nat/text2mel.py:27-28         pickle.load(duration)    -> vtts_load_duration
+ *   vietTTS/nat/gta.py:28-41              forward_fn(params, ...)  -> vtts_gta_host / vtts_acoustic_teacher_forward
  *
  * Conventions
  *   - plain C types only; no torch / CUDA types in signatures (`stream` is a
@@ -101,6 +102,16 @@ int vtts_acoustic_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_
                           const uint8_t* keep_mask_dev, int dropout_mode, uint64_t seed,
                           int B, int L, int N, float* mel_dev, void* stream);
 
+/* AcousticModel.__call__ (vietTTS/nat/model.py:146-169) with is_training=False, the teacher-forced pass gta.py:24-25 runs:
+ * mels_in_dev [B,N,80] is the ground-truth mel ALREADY shifted by one frame (gta.py:34-36).  keep_mask_dev uint8
+ * [B,N,2,256] prenet keep-masks (kept values x2); zone_mask_dev uint8 [B,N,4,512] zoneout masks in state order
+ * (h0, c0, h1, c1), 1 = keep the previous state (Bernoulli(0.1) in the reference, model.py:161-164); mode SEED draws
+ * both on the device, OFF disables both.  mel1 = projection output (may be NULL), mel2 = mel1 + postnet(mel1). */
+int vtts_acoustic_teacher_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev,
+                                  const float* dur_frames_dev, const int32_t* n_frames_dev, const float* mels_in_dev,
+                                  const uint8_t* keep_mask_dev, const uint8_t* zone_mask_dev, int dropout_mode, uint64_t seed,
+                                  int B, int L, int N, float* mel1_dev_or_null, float* mel2_dev, void* stream);
+
 /* DurationModel.__call__ (vietTTS/nat/model.py:64-70, is_training=False): TokenEncoder -> Linear(256) -> gelu(tanh
  * form, the jax default) -> Linear(1) -> softplus.  tokens_dev int32 [B,L]; lengths_dev int32 [B] or NULL (= L);
  * dur_sec_dev [B,L] predicted durations in SECONDS (0 past lengths[b]).  Row b equals the reference run on row b alone.
@@ -159,6 +170,14 @@ int vtts_tts_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, 
                   int dropout_mode, uint64_t seed, int max_frames, float* dur_sec_out, int32_t* n_frames_out,
                   int32_t* n_max_out, float* wav);
 int vtts_melspec_host(vtts_ctx* ctx, const float* wav, int B, int S, float* mel);
+/* forward_fn_ of vietTTS/nat/gta.py:28-41 (ground-truth-aligned mels for vocoder fine-tuning): wav_i16 int16 [B,S]
+ * (S % 256 == 0) -> /2^15 -> MelFilter -> shift by one frame -> teacher-forced acoustic model -> mel2_out [B,S/256,80].
+ * wav_lengths int32 [B] samples or NULL (= S): frames past wav_lengths[b]/256 are 0 (gta.py:74-75 slices them away);
+ * dur_sec [B,L] aligned phoneme durations in seconds; masks as in vtts_acoustic_teacher_forward;
+ * mel_gt_out_or_null [B,S/256,80] receives the MelFilter output.  Needs vtts_load_acoustic + vtts_load_mel_filterbank. */
+int vtts_gta_host(vtts_ctx* ctx, const int16_t* wav_i16, const int32_t* wav_lengths, const int32_t* tokens,
+                  const int32_t* lengths, const float* dur_sec, const uint8_t* keep_mask, const uint8_t* zone_mask,
+                  int dropout_mode, uint64_t seed, int B, int L, int S, float* mel_gt_out_or_null, float* mel2_out);
 
 /* ---- introspection for bench / tests ------------------------------------------------------ */
 /* number of kernel launches issued by this context since creation (our kernels only) */

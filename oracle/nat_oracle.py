@@ -13,6 +13,8 @@ arbiter for the float32 CUDA path.
   AcousticModel.inference    vietTTS/nat/model.py:123-144
   predict_mel                vietTTS/nat/text2mel.py:61-82
   DurationModel.__call__     vietTTS/nat/model.py:49-70
+  AcousticModel.__call__     vietTTS/nat/model.py:146-169   (teacher forced, zoneout)
+  forward_fn_ (GTA)          vietTTS/nat/gta.py:28-41
   text2mel post-processing   vietTTS/nat/text2mel.py:85-103
 
 dm-haiku semantics used (not vendored in the reference, setup.py:6-19):
@@ -248,3 +250,60 @@ def trim_end_silence(tokens, durations, mel, sil_index=0):
         silence_frame = int(end_silence * 16000 / 256)
         mel = mel[:, : (mel.shape[1] - silence_frame)]
     return mel
+
+
+# ---------------------------------------------------------------------------
+# teacher-forced pass with zoneout (model.py:146-169) and the GTA forward (gta.py:28-41)
+# ---------------------------------------------------------------------------
+def teacher_forced(ckpt, tokens, lengths, durations_frames, mels_in, keep_masks=None, zone_masks=None, dtype=torch.float32):
+    """AcousticModel(is_training=False).__call__(AcousticInput(...)).  tokens int [B,L]; lengths int [B];
+    durations [B,L] in frames; mels_in [B,N,80] = ground truth shifted by one frame (the caller does the shift,
+    gta.py:34-36).  keep_masks uint8 [B,N,2,256] (prenet dropout keep) or None; zone_masks uint8 [B,N,4,512] in the
+    state-tree order (layer0.hidden, layer0.cell, layer1.hidden, layer1.cell), 1 = keep previous state
+    (`s1 * m + s2 * (1 - m)`, model.py:157-159), or None.  Both mask sets are explicit INPUTS here; the reference
+    draws them from hk.next_rng_key().  Returns (mel1, mel2) = (projection, projection + postnet) as numpy [B,N,80]."""
+    P, S = ckpt["params"], ckpt["aux"]
+    with torch.no_grad():
+        mels_in = _t(mels_in, dtype)
+        B, N, _ = mels_in.shape
+        enc = token_encoder(P, S, tokens, lengths, dtype)
+        cond, _ = upsample(enc, _t(durations_frames, dtype), N)
+        if keep_masks is None:
+            p = prenet(P, mels_in, None, dtype)
+        else:
+            km = torch.as_tensor(np.asarray(keep_masks)).bool()          # [B,N,2,256] -> prenet wants [...,2,256] on dim 1
+            w1 = _t(P[A + "linear_1"]["w"], dtype)
+            w2 = _t(P[A + "linear_2"]["w"], dtype)
+            p = km[:, :, 0].to(dtype) * torch.relu(mels_in @ w1) / 0.5
+            p = km[:, :, 1].to(dtype) * torch.relu(p @ w2) / 0.5
+        x = torch.cat([cond, p], dim=-1)
+        w0, b0 = _t(P[A + "lstm/linear"]["w"], dtype), _t(P[A + "lstm/linear"]["b"], dtype)
+        w1_, b1 = _t(P[A + "lstm_1/linear"]["w"], dtype), _t(P[A + "lstm_1/linear"]["b"], dtype)
+        wo, bo = _t(P[A + "linear"]["w"], dtype), _t(P[A + "linear"]["b"], dtype)
+        H = w0.shape[1] // 4
+        h0 = x.new_zeros(B, H); c0 = x.new_zeros(B, H); h1 = x.new_zeros(B, H); c1 = x.new_zeros(B, H)
+        zm = None if zone_masks is None else torch.as_tensor(np.asarray(zone_masks)).bool()
+        outs = []
+        for t in range(N):
+            nh0, nc0 = lstm_step(x[:, t], h0, c0, w0, b0)
+            nh1, nc1 = lstm_step(torch.cat([x[:, t], nh0], dim=-1), h1, c1, w1_, b1)   # skip connection feeds the NEW h0
+            outs.append(torch.cat([nh0, nh1], dim=-1))                                  # decoder output = un-zoned states
+            if zm is None:
+                h0, c0, h1, c1 = nh0, nc0, nh1, nc1
+            else:
+                h0 = torch.where(zm[:, t, 0], h0, nh0); c0 = torch.where(zm[:, t, 1], c0, nc0)
+                h1 = torch.where(zm[:, t, 2], h1, nh1); c1 = torch.where(zm[:, t, 3], c1, nc1)
+        mel1 = torch.stack(outs, 1) @ wo + bo
+        mel2 = mel1 + postnet(P, S, mel1, dtype)
+        return mel1.numpy(), mel2.numpy()
+
+
+def gta_forward(ckpt, wav_i16, tokens, lengths, durations_sec, keep_masks=None, zone_masks=None, dtype=torch.float32):
+    """forward_fn_ (gta.py:28-41) for one padded batch: int16 wavs [B,S] -> (ground-truth mel, mel2_hat)."""
+    from . import mel_oracle
+    wav = np.asarray(wav_i16).astype(np.float32) / np.float32(2 ** 15)
+    mels = mel_oracle.mel_filter(wav)
+    inp = np.concatenate([np.zeros_like(mels[:, :1]), mels[:, :-1]], axis=1)
+    frames = (np.asarray(durations_sec, np.float32) * np.float32(16000)) / np.float32(256)
+    _, mel2 = teacher_forced(ckpt, tokens, lengths, frames, inp, keep_masks, zone_masks, dtype)
+    return mels, mel2

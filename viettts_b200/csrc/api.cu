@@ -445,6 +445,27 @@ int vtts_acoustic_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_
   return rc;
 }
 
+int vtts_acoustic_teacher_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev, const float* dur_frames_dev,
+                                  const int32_t* n_frames_dev, const float* mels_in_dev, const uint8_t* keep_mask_dev,
+                                  const uint8_t* zone_mask_dev, int dropout_mode, uint64_t seed, int B, int L, int N,
+                                  float* mel1_dev_or_null, float* mel2_dev, void* stream) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!tokens_dev || !dur_frames_dev || !mels_in_dev || !mel2_dev) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic_teacher_forward: null pointer");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need = 0;
+  int rc = vtts_acoustic_teacher_run(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, B, L, N, nullptr, nullptr, st,
+                                     nullptr, 0, &need);
+  if (rc) return rc;
+  rc = ctx->ensure_ws(need);
+  if (rc) return rc;
+  stage_begin(ctx, 1, st);
+  rc = vtts_acoustic_teacher_run(ctx, tokens_dev, lengths_dev, dur_frames_dev, n_frames_dev, mels_in_dev, keep_mask_dev, zone_mask_dev,
+                                 dropout_mode, seed, B, L, N, mel1_dev_or_null, mel2_dev, st, ctx->ws, ctx->ws_bytes, nullptr);
+  stage_end(ctx, 1, st);
+  return rc;
+}
+
 int vtts_duration_forward(vtts_ctx* ctx, const int32_t* tokens_dev, const int32_t* lengths_dev, int B, int L, float* dur_sec_dev,
                           void* stream) {
   if (!ctx) return VTTS_ERR_BAD_ARG;
@@ -628,6 +649,78 @@ int vtts_predict_duration_host(vtts_ctx* ctx, const int32_t* tokens, const int32
   VTTS_CUDA(cudaMemcpyAsync(hp + o_dur, dp + o_dur, dur_b, cudaMemcpyDeviceToHost, st));
   VTTS_CUDA(cudaStreamSynchronize(st));
   memcpy(dur_sec, hp + o_dur, dur_b);
+  return VTTS_OK;
+}
+
+namespace {
+__global__ void pcm16_to_float_kernel(const int16_t* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)in[i] * (1.0f / 32768.0f);                      // gta.py:32  wavs.astype(float32) / 2**15
+}
+}  // namespace
+
+// forward_fn_ of vietTTS/nat/gta.py:28-41: int16 waveform -> MelFilter -> ground-truth mel shifted by one frame ->
+// AcousticModel.__call__ (teacher forced, zoneout) -> mel2_hat.
+int vtts_gta_host(vtts_ctx* ctx, const int16_t* wav_i16, const int32_t* wav_lengths, const int32_t* tokens, const int32_t* lengths,
+                  const float* dur_sec, const uint8_t* keep_mask, const uint8_t* zone_mask, int dropout_mode, uint64_t seed, int B,
+                  int L, int S, float* mel_gt_out_or_null, float* mel2_out) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!wav_i16 || !tokens || !dur_sec || !mel2_out || B < 1 || L < 1 || S < 512 || S % vc::HOP)
+    return ctx->fail(VTTS_ERR_BAD_ARG, "gta_host: bad argument (S must be a multiple of %d, >= 512)", vc::HOP);
+  if (dropout_mode == VTTS_DROPOUT_MASK && (!keep_mask || !zone_mask)) return ctx->fail(VTTS_ERR_BAD_ARG, "gta_host: MASK mode needs both masks");
+  if (!ctx->mel_loaded) return ctx->fail(VTTS_ERR_NOT_LOADED, "gta_host: mel filterbank not loaded");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  const int N = S / vc::HOP;
+  Stager s;
+  const size_t wav_b = (size_t)B * S * 2, tok_b = (size_t)B * L * 4, len_b = (size_t)B * 4, dur_b = (size_t)B * L * 4, nf_b = (size_t)B * 4;
+  const size_t keep_b = dropout_mode == VTTS_DROPOUT_MASK ? (size_t)B * N * 2 * vc::PRENET : 0;
+  const size_t zone_b = dropout_mode == VTTS_DROPOUT_MASK ? (size_t)B * N * 4 * vc::DEC_H : 0;
+  const size_t mel_b = (size_t)B * N * vc::MEL * 4;
+  const size_t o_wav = s.take(wav_b), o_tok = s.take(tok_b), o_len = s.take(len_b), o_dur = s.take(dur_b), o_nf = s.take(nf_b);
+  const size_t o_keep = s.take(keep_b), o_zone = s.take(zone_b);
+  const size_t in_end = s.off;
+  const size_t o_gt = s.take(mel_b), o_out = s.take(mel_b);
+  const size_t host_end = s.off;
+  const size_t o_wavf = s.take((size_t)B * S * 4), o_in = s.take(mel_b);      // device-only scratch
+  int rc = ctx->ensure_staging(host_end, s.off);
+  if (rc) return rc;
+  char* hp = (char*)ctx->hpin;
+  char* dp = (char*)ctx->dstage;
+  cudaStream_t st = ctx->own_stream;
+  memcpy(hp + o_wav, wav_i16, wav_b);
+  memcpy(hp + o_tok, tokens, tok_b);
+  if (lengths) memcpy(hp + o_len, lengths, len_b);
+  {
+    float* d = (float*)(hp + o_dur);                                  // gta.py:37  durations * sample_rate / (n_fft // 4), float32
+    for (size_t i = 0; i < (size_t)B * L; ++i) d[i] = (dur_sec[i] * 16000.0f) / 256.0f;
+    int32_t* nf = (int32_t*)(hp + o_nf);                              // gta.py:74  l = wav_length // hop
+    for (int b = 0; b < B; ++b) {
+      int n = wav_lengths ? wav_lengths[b] / vc::HOP : N;
+      nf[b] = n < 1 ? 1 : (n > N ? N : n);
+    }
+  }
+  if (keep_b) memcpy(hp + o_keep, keep_mask, keep_b);
+  if (zone_b) memcpy(hp + o_zone, zone_mask, zone_b);
+  VTTS_CUDA(cudaMemcpyAsync(dp, hp, in_end, cudaMemcpyHostToDevice, st));
+  pcm16_to_float_kernel<<<148 * 4, 256, 0, st>>>((const int16_t*)(dp + o_wav), (float*)(dp + o_wavf), (size_t)B * S);
+  ctx->launches++;
+  VTTS_CUDA(cudaGetLastError());
+  rc = vtts_melspec(ctx, (const float*)(dp + o_wavf), B, S, (float*)(dp + o_gt), st);
+  if (rc) return rc;
+  // inp_mels = concat(zeros[B,1,D], mels[:, :-1]) (gta.py:34-36)
+  VTTS_CUDA(cudaMemsetAsync(dp + o_in, 0, mel_b, st));
+  if (N > 1)
+    VTTS_CUDA(cudaMemcpy2DAsync(dp + o_in + vc::MEL * 4, (size_t)N * vc::MEL * 4, dp + o_gt, (size_t)N * vc::MEL * 4,
+                                (size_t)(N - 1) * vc::MEL * 4, B, cudaMemcpyDeviceToDevice, st));
+  rc = vtts_acoustic_teacher_forward(ctx, (const int32_t*)(dp + o_tok), lengths ? (const int32_t*)(dp + o_len) : nullptr,
+                                     (const float*)(dp + o_dur), (const int32_t*)(dp + o_nf), (const float*)(dp + o_in),
+                                     keep_b ? (const uint8_t*)(dp + o_keep) : nullptr, zone_b ? (const uint8_t*)(dp + o_zone) : nullptr,
+                                     dropout_mode, seed, B, L, N, nullptr, (float*)(dp + o_out), st);
+  if (rc) return rc;
+  VTTS_CUDA(cudaMemcpyAsync(hp + o_gt, dp + o_gt, 2 * mel_b + (o_out - o_gt - mel_b), cudaMemcpyDeviceToHost, st));
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  if (mel_gt_out_or_null) memcpy(mel_gt_out_or_null, hp + o_gt, mel_b);
+  memcpy(mel2_out, hp + o_out, mel_b);
   return VTTS_OK;
 }
 

@@ -106,7 +106,7 @@ __global__ void repack_proj_kernel(const float* __restrict__ src, float* __restr
 constexpr int UP_F = 8;  // frames per CTA
 __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ enc, const float* __restrict__ dur,
                                                        const int32_t* __restrict__ lengths, const int32_t* __restrict__ n_frames,
-                                                       int L, int N, float* __restrict__ out) {
+                                                       int L, int N, float* __restrict__ out, int out_ld) {
   extern __shared__ float sm[];
   float* mid = sm;            // [L]
   float* w = sm + L;          // [UP_F][L]
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__
     const int n = f0 + f;
     if (n < nf) {
       float2 o = make_float2(acc[f][0], acc[f][1]);
-      *reinterpret_cast<float2*>(out + ((size_t)b * N + n) * vc::ENC_OUT + tid * 2) = o;
+      *reinterpret_cast<float2*>(out + ((size_t)b * N + n) * out_ld + tid * 2) = o;
     }
   }
 }
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) enc_scan_kernel(const EncScan
 }
 
 // same, accumulating two K segments (xa: 64*SLA columns with weights wa; xb: 64*SLB columns with wb) before ONE reduction
-template <int SLA, int SLB>
+template <int SLA, int SLB, int PITCH = DEC_KPAD>
 __device__ __forceinline__ void dec_matmul2(const float* __restrict__ xa, const float (&wa)[SLA][4], const float* __restrict__ xb,
                                             const float (&wb)[SLB][4], int ngroups, float* part, float* zout, const float* zadd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -421,12 +421,12 @@ __device__ __forceinline__ void dec_matmul2(const float* __restrict__ xa, const 
     float acc[RG][4];
 #pragma unroll
     for (int r = 0; r < RG; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-    const float* xk = xa + (size_t)(g * RG) * DEC_KPAD + ks * SLA;
+    const float* xk = xa + (size_t)(g * RG) * PITCH + ks * SLA;
 #pragma unroll
     for (int kk = 0; kk < SLA; kk += 4) {
 #pragma unroll
       for (int r = 0; r < RG; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)r * DEC_KPAD + kk);
+        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)r * PITCH + kk);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           acc[r][c] = fmaf(xv.x, wa[kk + 0][c], acc[r][c]);
@@ -436,12 +436,12 @@ __device__ __forceinline__ void dec_matmul2(const float* __restrict__ xa, const 
         }
       }
     }
-    const float* xk2 = xb + (size_t)(g * RG) * DEC_KPAD + ks * SLB;
+    const float* xk2 = xb + (size_t)(g * RG) * PITCH + ks * SLB;
 #pragma unroll
     for (int kk = 0; kk < SLB; kk += 4) {
 #pragma unroll
       for (int r = 0; r < RG; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(xk2 + (size_t)r * DEC_KPAD + kk);
+        const float4 xv = *reinterpret_cast<const float4*>(xk2 + (size_t)r * PITCH + kk);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           acc[r][c] = fmaf(xv.x, wb[kk + 0][c], acc[r][c]);
@@ -769,6 +769,130 @@ __global__ void precompose_kernel(const float* __restrict__ wo, const float* __r
   }
 }
 
+// ---- teacher-forced decoder scan with zoneout (AcousticModel.__call__, model.py:146-169) ------------------
+// The prenet and every input-side product are hoisted out of the recurrence (teacher forcing: the decoder input of
+// frame t is the ground-truth frame t-1), so the scan only carries  h0s.W0[h0 rows],  h0n.W1[h0 rows]  and
+// h1s.W1[h1 rows].  *n = the cores' new state (what the decoder outputs), *s = the state after zoneout
+// (state = mask ? previous : new, model.py:157-159).  One grid barrier per frame: iteration s runs LSTM0 of frame s
+// and LSTM1 of frame s-1 -- both only need values published in iteration s-1.
+struct TfScanArgs {
+  const float* zc0;      // [B][N][2048]  [cond, p2] . W0[0:768] + b0
+  const float* zc1;      // [B][N][2048]  [cond, p2] . W1[0:768] + b1
+  const float* w0r;      // [128][768][16]   rows 512..1279 of lstm0 ([p2, h0]); only the h0 rows are used here
+  const float* w1r;      // [128][1280][16]  rows 512..1791 of lstm1 ([p2, h0, h1]); h0 and h1 rows used
+  const uint8_t* zone;   // [B][N][4][512] (h0, c0, h1, c1; 1 = keep the previous state) or null
+  uint64_t seed;
+  int mode;              // VTTS_DROPOUT_OFF / MASK / SEED
+  float* h0s;            // [2][B][512] zoned hidden state of layer 0, double buffered by frame parity
+  float* h1s;            // [2][B][512]
+  float* hout;           // [B][N][1024]  decoder outputs [h0n | h1n]
+  int B, N;
+  int row_base;
+};
+
+constexpr int TF_PITCH = 3 * vc::DEC_H + 4;    // [h0s | h0n | h1s] + pad
+
+// true = keep the previous state.  SEED mode: Bernoulli(0.1) from the same threefry stream as the prenet masks,
+// counter word 1 offset past the prenet's 2*256 entries.
+__device__ __forceinline__ bool zone_keep(int mode, const uint8_t* zone, uint64_t seed, int b, int t, int N, int which, int unit) {
+  if (mode == VTTS_DROPOUT_OFF) return false;
+  if (mode == VTTS_DROPOUT_MASK) return zone[(((size_t)b * N + t) * 4 + which) * vc::DEC_H + unit] != 0;
+  uint32_t o0, o1;
+  threefry2x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(b * (uint32_t)N + t), (uint32_t)(2 * vc::PRENET + which * vc::DEC_H + unit), o0, o1);
+  return o0 < 429496730u;   // 0.1 * 2^32
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_tf_scan_kernel(const TfScanArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float sm[];
+  constexpr int H = vc::DEC_H, K0 = vc::PRENET + H, K1 = vc::PRENET + 2 * H, SLH = H / NSLICE;   // 8
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int B = a.B, N = a.N;
+  float* xs = sm;                                   // [DEC_XR][TF_PITCH]
+  float* part = xs + DEC_XR * TF_PITCH;             // [8][DEC_XR][16]
+  float* zs = part + 8 * DEC_XR * NCOL;             // [DEC_XR][16]
+  float* cst = zs + DEC_XR * NCOL;                  // [2][DEC_XR][UPC] zoned cell states of the CTA's units
+  const int ks = tid >> 2, cgp = tid & 3;
+  float w0h[SLH][4], w1h0[SLH][4], w1h1[SLH][4];
+  {
+    auto ld = [&](float (&dst)[4], const float* base, int row) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * NCOL + cgp * 4));
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    };
+    const float* g0 = a.w0r + (size_t)c * K0 * NCOL;
+    const float* g1 = a.w1r + (size_t)c * K1 * NCOL;
+#pragma unroll
+    for (int i = 0; i < SLH; ++i) {
+      ld(w0h[i], g0, vc::PRENET + ks * SLH + i);
+      ld(w1h0[i], g1, vc::PRENET + ks * SLH + i);
+      ld(w1h1[i], g1, vc::PRENET + H + ks * SLH + i);
+    }
+  }
+  for (int e = tid; e < 2 * DEC_XR * UPC; e += SCAN_THREADS) cst[e] = 0.f;
+  for (int e = tid; e < DEC_XR * TF_PITCH; e += SCAN_THREADS) xs[e] = 0.f;
+  __syncthreads();
+  const int ngroups = (B + RG - 1) / RG;
+  for (int s = 0; s <= N; ++s) {
+    // values published in iteration s-1: h0s_{s-1}, h0n_{s-1} (LSTM0 of frame s-1) and h1s_{s-2} (LSTM1 of frame s-2)
+    if (s >= 1) {
+      dec_fetch(xs, TF_PITCH, 0, a.h0s + (size_t)((s - 1) & 1) * B * H, H, H, B);
+      dec_fetch(xs, TF_PITCH, H, a.hout + (size_t)(s - 1) * 2 * H, H, N * 2 * H, B);
+    }
+    if (s >= 2) dec_fetch(xs, TF_PITCH, 2 * H, a.h1s + (size_t)(s & 1) * B * H, H, H, B);
+    __syncthreads();
+    if (s < N) {
+      // ---- LSTM0 of frame s: z = zc0[s] + h0s_{s-1} . W0[h0 rows] ----
+      dec_matmul<SLH, TF_PITCH>(xs, w0h, ngroups, part, zs, nullptr);
+      if (tid < B * UPC) {
+        const int r = tid / UPC, uu = tid % UPC, u = c * UPC + uu;
+        const float* zc = a.zc0 + ((size_t)r * N + s) * (4 * H) + u;
+        const float c_prev = cst[r * UPC + uu];
+        float cc = c_prev;
+        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
+        const bool kh = zone_keep(a.mode, a.zone, a.seed, a.row_base + r, s, N, 0, u);
+        const bool kc = zone_keep(a.mode, a.zone, a.seed, a.row_base + r, s, N, 1, u);
+        a.hout[((size_t)r * N + s) * 2 * H + u] = h;
+        a.h0s[((size_t)(s & 1) * B + r) * H + u] = kh ? xs[(size_t)r * TF_PITCH + u] : h;
+        cst[r * UPC + uu] = kc ? c_prev : cc;
+      }
+    }
+    if (s >= 1) {
+      // ---- LSTM1 of frame s-1: z = zc1[s-1] + h0n_{s-1} . W1[h0 rows] + h1s_{s-2} . W1[h1 rows] ----
+      const int t = s - 1;
+      __syncthreads();    // zs is reused
+      dec_matmul2<SLH, SLH, TF_PITCH>(xs + H, w1h0, xs + 2 * H, w1h1, ngroups, part, zs, nullptr);
+      if (tid < B * UPC) {
+        const int r = tid / UPC, uu = tid % UPC, u = c * UPC + uu;
+        const float* zc = a.zc1 + ((size_t)r * N + t) * (4 * H) + u;
+        const float c_prev = cst[(DEC_XR + r) * UPC + uu];
+        float cc = c_prev;
+        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
+        const bool kh = zone_keep(a.mode, a.zone, a.seed, a.row_base + r, t, N, 2, u);
+        const bool kc = zone_keep(a.mode, a.zone, a.seed, a.row_base + r, t, N, 3, u);
+        a.hout[((size_t)r * N + t) * 2 * H + H + u] = h;
+        a.h1s[((size_t)(t & 1) * B + r) * H + u] = kh ? xs[(size_t)r * TF_PITCH + 2 * H + u] : h;
+        cst[(DEC_XR + r) * UPC + uu] = kc ? c_prev : cc;
+      }
+    }
+    __syncthreads();
+    grid.sync();
+  }
+}
+
+// out[row][c] (row stride out_ld) = relu(x[row][c]) * keep_scale  -- the two prenet dropouts applied to whole sequences
+__global__ void prenet_act_kernel(const float* __restrict__ x, const uint8_t* __restrict__ keep, uint64_t seed, int mode, int layer,
+                                  int B, int N, float* __restrict__ out, int out_ld) {
+  const size_t total = (size_t)B * N * vc::PRENET;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % vc::PRENET);
+    const size_t row = i / vc::PRENET;
+    const int b = (int)(row / N), t = (int)(row % N);
+    out[row * out_ld + u] = fmaxf(x[i], 0.f) * keep_scale(mode, keep, seed, b, t, N, layer, u);
+  }
+}
+
+constexpr size_t tf_scan_smem() { return ((size_t)DEC_XR * TF_PITCH + 8 * DEC_XR * NCOL + DEC_XR * NCOL + 2 * DEC_XR * UPC) * 4; }
+
 constexpr size_t enc_scan_smem() {
   return ((size_t)32 * (vc::ENC_D + 4) + 8 * DEC_XR * NCOL + DEC_XR * NCOL + MAX_ROWS * UPC) * 4;
 }
@@ -792,6 +916,7 @@ enum {
   D_DEC_BC,      // [256]
   D_DEC_WP2,     // [128][256][2]
   D_DEC_WO,      // [4][3][1088][8] (20 columns used per CTA)
+  D_ZERO,        // [2048] zeros: bias of the bias-free prenet linears (model.py:88-89) on the generic conv path
   D_COUNT
 };
 
@@ -856,7 +981,7 @@ static int run_token_encoder(vtts_ctx* ctx, const EncWeights& w, const int32_t* 
 int vtts_acoustic_prepare(vtts_ctx* ctx) {
   const size_t sizes[D_COUNT] = {256, 256, 256, 512, 512, 512, 512,
                                  (size_t)2 * 64 * 256 * 16, (size_t)128 * 768 * 16, (size_t)128 * 1280 * 16,
-                                 (size_t)16 * 1024 * 16, (size_t)1024 * 256, 256, (size_t)16 * 256 * 16, (size_t)4 * 3 * 1088 * 8};
+                                 (size_t)16 * 1024 * 16, (size_t)1024 * 256, 256, (size_t)16 * 256 * 16, (size_t)4 * 3 * 1088 * 8, 2048};
   size_t total = 0;
   std::vector<size_t> offs(D_COUNT);
   for (int i = 0; i < D_COUNT; ++i) {
@@ -880,6 +1005,7 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
   repack_cols_kernel<<<256, 256>>>(ctx->ac_d[D_DEC_WCFULL], 256, 0, 1024, ctx->ac_d[D_DEC_WC], 16, 16, 16, 0);
   repack_cols_kernel<<<64, 256>>>(T[aci::PRE2_W], 256, 0, 256, ctx->ac_d[D_DEC_WP2], 16, 16, 16, 0);
   VTTS_CUDA(cudaMemset(ctx->ac_d[D_DEC_WO], 0, (size_t)4 * 3 * 1088 * 8 * sizeof(float)));
+  VTTS_CUDA(cudaMemset(ctx->ac_d[D_ZERO], 0, 2048 * sizeof(float)));
   repack_proj_kernel<<<64, 256>>>(T[aci::PROJ_W], ctx->ac_d[D_DEC_WO]);
   VTTS_CUDA(cudaGetLastError());
   // ---- tensor-core packed weights of the convs and hoisted GEMMs ----
@@ -907,6 +1033,38 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
   VTTS_CUDA(cudaDeviceSynchronize());
   VTTS_CUDA(cudaFuncSetAttribute(enc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_scan_smem()));
   VTTS_CUDA(cudaFuncSetAttribute(decoder_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_scan_smem()));
+  VTTS_CUDA(cudaFuncSetAttribute(decoder_tf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_scan_smem()));
+  return VTTS_OK;
+}
+
+// AcousticModel.postnet (model.py:113-121, is_training=False) + the residual add (:143-144 / :169):
+// mel = melpre + conv5(tanh(bn(conv5(...))));  q0/q1 are [B*N][512] scratch
+static int run_postnet(vtts_ctx* ctx, const float* melpre, const int32_t* n_frames, int B, int N, float* q0, float* q1, float* mel,
+                       cudaStream_t st) {
+  auto& T = ctx->ac_t;
+  auto& D = ctx->ac_d;
+  ConvLaunch Lc;
+  const float* pin = melpre;
+  float* pout = q0;
+  int cin = 80;
+  for (int i = 0; i < 5; ++i) {
+    const int cout = i < 4 ? 512 : 80;
+    memset(&Lc, 0, sizeof(Lc));
+    Lc.nprob = 1; Lc.Cin = cin; Lc.Cout = cout; Lc.B = B; Lc.T_rows = N; Lc.rows_out = N;
+    Lc.len = n_frames; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = i < 4 ? 1 : 0;
+    ConvProb p;
+    memset(&p, 0, sizeof(p));
+    p.x0 = pin; p.w = T[aci::POST_CONV(i, 0)]; p.bias = T[aci::POST_CONV(i, 1)];
+    if (i < 4) { p.bn_mean = T[aci::POST_CONV(i, 4)]; p.bn_inv = D[D_POST_BNINV0 + i]; p.bn_off = T[aci::POST_CONV(i, 3)]; }
+    if (i == 4) { p.resid = melpre; p.out = mel; } else { p.out = pout; }
+    p.k = 5; p.dil = 1; p.in_off = -2; p.out_stride = 1; p.out_off = 0;
+    Lc.p[0] = p;
+    int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[i == 0 ? WP_POST0 : (i == 1 ? WP_POST1 : (i == 2 ? WP_POST2 : (i == 3 ? WP_POST3 : WP_POST4)))], st);
+    if (rc) return rc;
+    pin = pout;
+    pout = (pout == q0) ? q1 : q0;
+    cin = cout;
+  }
   return VTTS_OK;
 }
 
@@ -971,7 +1129,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     size_t smem = (size_t)(L + UP_F * L) * sizeof(float);
     if (smem > 200 * 1024) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: L=%d too long for the upsample kernel", L);
     if (smem > 48 * 1024) VTTS_CUDA(cudaFuncSetAttribute(upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    upsample_kernel<<<grid, 256, smem, st>>>(enc, dur, lengths, n_frames, L, N, cond);
+    upsample_kernel<<<grid, 256, smem, st>>>(enc, dur, lengths, n_frames, L, N, cond, vc::ENC_OUT);
     ctx->launches++;
     VTTS_CUDA(cudaGetLastError());
   }
@@ -999,29 +1157,131 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(DEC_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
     ctx->launches++;
   }
-  // ---- postnet: 4 x [conv k5, BN, tanh], conv k5, + residual ----
-  const float* pin = melpre;
-  float* pout = q0;
-  int cin = 80;
-  for (int i = 0; i < 5; ++i) {
-    const int cout = i < 4 ? 512 : 80;
-    memset(&Lc, 0, sizeof(Lc));
-    Lc.nprob = 1; Lc.Cin = cin; Lc.Cout = cout; Lc.B = B; Lc.T_rows = N; Lc.rows_out = N;
-    Lc.len = n_frames; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = i < 4 ? 1 : 0;
-    ConvProb p;
-    memset(&p, 0, sizeof(p));
-    p.x0 = pin; p.w = T[aci::POST_CONV(i, 0)]; p.bias = T[aci::POST_CONV(i, 1)];
-    if (i < 4) { p.bn_mean = T[aci::POST_CONV(i, 4)]; p.bn_inv = D[D_POST_BNINV0 + i]; p.bn_off = T[aci::POST_CONV(i, 3)]; }
-    if (i == 4) { p.resid = melpre; p.out = mel; } else { p.out = pout; }
-    p.k = 5; p.dil = 1; p.in_off = -2; p.out_stride = 1; p.out_off = 0;
-    Lc.p[0] = p;
-    rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[i == 0 ? WP_POST0 : (i == 1 ? WP_POST1 : (i == 2 ? WP_POST2 : (i == 3 ? WP_POST3 : WP_POST4)))], st);
-    if (rc) return rc;
-    pin = pout;
-    pout = (pout == q0) ? q1 : q0;
-    cin = cout;
-  }
+  rc = run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel, st);
+  if (rc) return rc;
   return VTTS_OK;
+}
+
+// AcousticModel.__call__ (model.py:146-169) with is_training=False, as gta.py:24-25 (`val_net`) runs it:
+// encoder -> upsample to the mel length -> prenet of the SHIFTED ground-truth mel (dropout live) -> zoneout decoder
+// scan -> projection -> postnet.  mel1 = projection output (may be null), mel2 = mel1 + postnet(mel1).
+int vtts_acoustic_teacher_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur,
+                              const int32_t* n_frames, const float* mels_in, const uint8_t* keep, const uint8_t* zone, int mode,
+                              uint64_t seed, int B, int L, int N, float* mel1, float* mel2, cudaStream_t st, void* ws_base,
+                              size_t ws_cap, size_t* ws_need) {
+  const bool measure = ws_need != nullptr;
+  if (!measure) {
+    if (!ctx->ac_loaded) return ctx->fail(VTTS_ERR_NOT_LOADED, "acoustic weights not loaded");
+    if (B < 1 || L < 1 || N < 1 || B > MAX_ROWS)
+      return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic (teacher forced): B=%d L=%d N=%d (1 <= B <= %d rows per call)", B, L, N, MAX_ROWS);
+    if (mode < 0 || mode > 2) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic (teacher forced): dropout_mode %d", mode);
+    if (mode == VTTS_DROPOUT_MASK && (!keep || !zone))
+      return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic (teacher forced): dropout_mode MASK needs keep_mask and zone_mask");
+    if (ctx->sm_count < SCAN_CTAS) return ctx->fail(VTTS_ERR_NO_DEVICE, "scan kernels need %d SMs, device has %d", SCAN_CTAS, ctx->sm_count);
+  }
+  Arena ar(ws_base, ws_cap, measure);
+  const size_t BL = (size_t)B * L, BN = (size_t)B * N;
+  constexpr int XW = vc::ENC_OUT + vc::PRENET;   // 768: decoder input [cond | prenet(mel)]
+  float* e0 = ar.take<float>(BL * 256);
+  float* e1 = ar.take<float>(BL * 256);
+  float* zx = ar.take<float>(2 * BL * 1024);
+  float* enc = ar.take<float>(BL * 512);
+  float* xin = ar.take<float>(BN * XW);
+  float* pa = ar.take<float>(BN * 256);
+  float* pb = ar.take<float>(BN * 256);
+  float* zc0 = ar.take<float>(BN * 2048);
+  float* zc1 = ar.take<float>(BN * 2048);
+  float* hout = ar.take<float>(BN * 1024);
+  float* melpre = ar.take<float>(BN * 80);
+  float* q0 = ar.take<float>(BN * 512);
+  float* q1 = ar.take<float>(BN * 512);
+  float* h0s = ar.take<float>((size_t)2 * DEC_XR * 512);
+  float* h1s = ar.take<float>((size_t)2 * DEC_XR * 512);
+  if (measure) {
+    *ws_need = ar.off + 256;
+    return VTTS_OK;
+  }
+  auto& T = ctx->ac_t;
+  auto& D = ctx->ac_d;
+  ctx->tap_enc = enc; ctx->tap_enc_n = BL * 512;
+  ctx->tap_cond = nullptr; ctx->tap_cond_n = 0;
+  ctx->tap_melpre = melpre; ctx->tap_melpre_n = BN * 80;
+  VTTS_CUDA(cudaMemsetAsync(mel2, 0, BN * 80 * sizeof(float), st));
+  if (mel1) VTTS_CUDA(cudaMemsetAsync(mel1, 0, BN * 80 * sizeof(float), st));
+  VTTS_CUDA(cudaMemsetAsync(xin, 0, BN * XW * sizeof(float), st));
+  VTTS_CUDA(cudaMemsetAsync(melpre, 0, BN * 80 * sizeof(float), st));
+  {
+    EncWeights ew;
+    ew.embed = T[aci::EMBED];
+    for (int i = 0; i < 3; ++i) {
+      ew.conv_w[i] = T[aci::ENC_CONV(i, 0)]; ew.conv_b[i] = T[aci::ENC_CONV(i, 1)];
+      ew.bn_off[i] = T[aci::ENC_CONV(i, 3)]; ew.bn_mean[i] = T[aci::ENC_CONV(i, 4)]; ew.bn_inv[i] = D[D_ENC_BNINV0 + i];
+    }
+    ew.lf_w = T[aci::ENC_LSTM_F_W]; ew.lf_b = T[aci::ENC_LSTM_F_B]; ew.lb_w = T[aci::ENC_LSTM_B_W]; ew.lb_b = T[aci::ENC_LSTM_B_B];
+    ew.whr = D[D_ENC_WHR]; ew.wpk_conv = &ctx->ac_wpk_t[WP_ENC]; ew.wpk_hoist = &ctx->ac_wpk_t[WP_ENCH];
+    int rc = run_token_encoder(ctx, ew, tokens, lengths, B, L, e0, e1, zx, enc, st);
+    if (rc) return rc;
+  }
+  {  // cond -> columns 0..511 of the decoder input
+    dim3 grid((N + UP_F - 1) / UP_F, B);
+    size_t smem = (size_t)(L + UP_F * L) * sizeof(float);
+    if (smem > 200 * 1024) return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: L=%d too long for the upsample kernel", L);
+    if (smem > 48 * 1024) VTTS_CUDA(cudaFuncSetAttribute(upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upsample_kernel<<<grid, 256, smem, st>>>(enc, dur, lengths, n_frames, L, N, xin, XW);
+    ctx->launches++;
+    VTTS_CUDA(cudaGetLastError());
+  }
+  // ---- prenet over the whole sequence (model.py:95-100,149): two bias-free linears, relu, dropout 0.5 each ----
+  ConvLaunch Lc;
+  auto gemm = [&](const float* x, const float* w, const float* bias, float* out, int cin, int cout) {
+    memset(&Lc, 0, sizeof(Lc));
+    Lc.nprob = 1; Lc.Cin = cin; Lc.Cout = cout; Lc.B = 1; Lc.T_rows = (int)BN; Lc.rows_out = (int)BN;
+    Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0; Lc.len_mul = 1;
+    Lc.p[0] = ConvProb{x, nullptr, nullptr, w, bias, nullptr, nullptr, nullptr, nullptr, out, 1, 1, 0, 1, 0};
+    return vtts_launch_conv(ctx, Lc, st);
+  };
+  const size_t act_blocks = (BN * 256 + 255) / 256;
+  const unsigned act_grid = (unsigned)(act_blocks < 148 * 16 ? act_blocks : 148 * 16);
+  int rc = gemm(mels_in, T[aci::PRE1_W], D[D_ZERO], pa, 80, 256);
+  if (rc) return rc;
+  prenet_act_kernel<<<act_grid, 256, 0, st>>>(pa, keep, seed, mode, 0, B, N, pb, 256);
+  ctx->launches++;
+  rc = gemm(pb, T[aci::PRE2_W], D[D_ZERO], pa, 256, 256);
+  if (rc) return rc;
+  prenet_act_kernel<<<act_grid, 256, 0, st>>>(pa, keep, seed, mode, 1, B, N, xin + vc::ENC_OUT, XW);
+  ctx->launches++;
+  VTTS_CUDA(cudaGetLastError());
+  // ---- every input-side product of both LSTMs in one launch: zc = [cond | p2] . W[0:768] + b ----
+  memset(&Lc, 0, sizeof(Lc));
+  Lc.nprob = 2; Lc.Cin = XW; Lc.Cout = 2048; Lc.B = 1; Lc.T_rows = (int)BN; Lc.rows_out = (int)BN;
+  Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0; Lc.len_mul = 1;
+  Lc.p[0] = ConvProb{xin, nullptr, nullptr, T[aci::DEC_L0_W], T[aci::DEC_L0_B], nullptr, nullptr, nullptr, nullptr, zc0, 1, 1, 0, 1, 0};
+  Lc.p[1] = ConvProb{xin, nullptr, nullptr, T[aci::DEC_L1_W], T[aci::DEC_L1_B], nullptr, nullptr, nullptr, nullptr, zc1, 1, 1, 0, 1, 0};
+  rc = vtts_launch_conv(ctx, Lc, st);
+  if (rc) return rc;
+  // ---- zoneout scan, <= 32 rows per launch ----
+  for (int b0 = 0; b0 < B; b0 += DEC_XR) {
+    const int nb = B - b0 < DEC_XR ? B - b0 : DEC_XR;
+    TfScanArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.zc0 = zc0 + (size_t)b0 * N * 2048; ta.zc1 = zc1 + (size_t)b0 * N * 2048;
+    ta.w0r = D[D_DEC_W0R]; ta.w1r = D[D_DEC_W1R];
+    ta.zone = zone; ta.seed = seed; ta.mode = mode;
+    ta.h0s = h0s; ta.h1s = h1s; ta.hout = hout + (size_t)b0 * N * 1024;
+    ta.B = nb; ta.N = N; ta.row_base = b0;
+    void* args[] = {&ta};
+    VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_tf_scan_kernel, dim3(SCAN_CTAS), dim3(SCAN_THREADS), args, tf_scan_smem(), st));
+    ctx->launches++;
+  }
+  // ---- projection over all frames, then the postnet ----
+  memset(&Lc, 0, sizeof(Lc));
+  Lc.nprob = 1; Lc.Cin = 1024; Lc.Cout = 80; Lc.B = B; Lc.T_rows = N; Lc.rows_out = N;
+  Lc.len = n_frames; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;      // rows past n_frames[b] stay 0
+  Lc.p[0] = ConvProb{hout, nullptr, nullptr, T[aci::PROJ_W], T[aci::PROJ_B], nullptr, nullptr, nullptr, nullptr, melpre, 1, 1, 0, 1, 0};
+  rc = vtts_launch_conv(ctx, Lc, st);
+  if (rc) return rc;
+  if (mel1) VTTS_CUDA(cudaMemcpyAsync(mel1, melpre, BN * 80 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel2, st);
 }
 
 // =====================================================================================================

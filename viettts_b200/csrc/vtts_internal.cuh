@@ -251,6 +251,10 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
                       float* mel, cudaStream_t st, void* ws_base, size_t ws_cap, size_t* ws_need);
 // melspec.cu
 int vtts_melspec_prepare(vtts_ctx* ctx);
+int vtts_acoustic_teacher_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const float* dur,
+                              const int32_t* n_frames, const float* mels_in, const uint8_t* keep, const uint8_t* zone, int mode,
+                              uint64_t seed, int B, int L, int N, float* mel1, float* mel2, cudaStream_t st, void* ws_base,
+                              size_t ws_cap, size_t* ws_need);
 int vtts_duration_prepare(vtts_ctx* ctx);
 // DurationModel.__call__ (model.py:64-70); dur_sec [B][L] seconds, 0 past lengths[b]
 int vtts_duration_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths, int B, int L, float* dur_sec,

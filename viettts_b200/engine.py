@@ -344,6 +344,69 @@ class Engine:
                 out[i] = wav[r, : nfs[i] * config.HOP].copy()
         return out
 
+    def _tf_masks(self, B, N, keep_masks, zone_masks, seed):
+        if keep_masks is not None or zone_masks is not None:
+            if keep_masks is None or zone_masks is None:
+                raise ValueError("keep_masks and zone_masks must be given together")
+            km = _np(keep_masks, np.uint8, (B, N, 2, config.PRENET_DIM), "keep_masks")
+            zm = _np(zone_masks, np.uint8, (B, N, 4, config.ACOUSTIC_DECODER_DIM), "zone_masks")
+            return km, zm, DROPOUT_MASK
+        return None, None, (DROPOUT_SEED if seed is not None else DROPOUT_OFF)
+
+    def teacher_forced(self, tokens, dur_frames, mels_in, lengths=None, n_frames=None, keep_masks=None, zone_masks=None, seed=None):
+        """AcousticModel.__call__ (nat/model.py:146-169, is_training=False): tokens int [B,L], durations in frames
+        [B,L], mels_in f32 [B,N,80] (ground truth shifted by one frame) -> (mel1, mel2) f32 [B,N,80].
+        keep_masks uint8 [B,N,2,256] / zone_masks uint8 [B,N,4,512] (1 = keep previous state), else `seed` for the
+        on-device stream, else both off.  Host buffers; the device work is vtts_acoustic_teacher_forward."""
+        import torch
+        tokens = _np(tokens, np.int32)
+        B, L = tokens.shape
+        mels_in = _np(mels_in, np.float32)
+        N = mels_in.shape[1]
+        if mels_in.shape != (B, N, config.MEL_DIM):
+            raise ValueError(f"mels_in must be [B,N,{config.MEL_DIM}]")
+        if B > MAX_ACOUSTIC_ROWS:
+            raise ValueError(f"teacher_forced: at most {MAX_ACOUSTIC_ROWS} rows per call")
+        km, zm, mode = self._tf_masks(B, N, keep_masks, zone_masks, seed)
+        dev = torch.device("cuda", self.device)
+        up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+        t_tok, t_dur, t_in = up(tokens), up(_np(dur_frames, np.float32, (B, L), "durations")), up(mels_in)
+        t_len = up(None if lengths is None else _np(lengths, np.int32, (B,), "lengths"))
+        t_nf = up(None if n_frames is None else _np(n_frames, np.int32, (B,), "n_frames"))
+        t_km, t_zm = up(km), up(zm)
+        m1 = torch.empty((B, N, config.MEL_DIM), dtype=torch.float32, device=dev)
+        m2 = torch.empty_like(m1)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ck(self.lib.vtts_acoustic_teacher_forward(self.h, _ptr(t_tok), _ptr(t_len), _ptr(t_dur), _ptr(t_nf), _ptr(t_in), _ptr(t_km),
+                                                        _ptr(t_zm), mode, int(seed or 0), B, L, N, _ptr(m1), _ptr(m2), st))
+        torch.cuda.synchronize(dev)
+        return m1.cpu().numpy(), m2.cpu().numpy()
+
+    def gta(self, wav_i16, tokens, dur_sec, lengths=None, wav_lengths=None, keep_masks=None, zone_masks=None, seed=None, return_gt=False):
+        """forward_fn of nat/gta.py:28-44 in one library call: int16 wavs [B,S] + aligned phonemes -> mel2_hat
+        f32 [B,S/256,80] (rows past wav_lengths[b]//256 are 0)."""
+        if not self._mel_loaded:
+            self.load_mel_filterbank()
+        wav = np.ascontiguousarray(np.asarray(wav_i16))
+        if wav.dtype != np.int16 or wav.ndim != 2:
+            raise ValueError("wav_i16 must be int16 [B,S]")
+        B, S = wav.shape
+        tokens = _np(tokens, np.int32)
+        if tokens.ndim != 2 or tokens.shape[0] != B:
+            raise ValueError("tokens must be [B,L]")
+        L = tokens.shape[1]
+        if B > MAX_ACOUSTIC_ROWS:
+            raise ValueError(f"gta: at most {MAX_ACOUSTIC_ROWS} rows per call")
+        N = S // config.HOP
+        km, zm, mode = self._tf_masks(B, N, keep_masks, zone_masks, seed)
+        lens = None if lengths is None else _np(lengths, np.int32, (B,), "lengths")
+        wl = None if wav_lengths is None else _np(wav_lengths, np.int32, (B,), "wav_lengths")
+        gt = np.empty((B, N, config.MEL_DIM), np.float32) if return_gt else None
+        out = np.empty((B, N, config.MEL_DIM), np.float32)
+        self._ck(self.lib.vtts_gta_host(self.h, _ptr(wav), _ptr(wl), _ptr(tokens), _ptr(lens), _ptr(_np(dur_sec, np.float32, (B, L), "durations")),
+                                        _ptr(km), _ptr(zm), mode, int(seed or 0), B, L, S, _ptr(gt), _ptr(out)))
+        return (out, gt) if return_gt else out
+
     def melspec(self, wav) -> np.ndarray:
         """MelFilter.__call__ (nat/dsp.py:115-128): wav f32 [B,S] -> log-mel [B,S/256,80]."""
         if not self._mel_loaded:
