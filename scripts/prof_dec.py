@@ -17,6 +17,6 @@ for B in (1, 8, 32, 64):
     ms = eng.last_stage_ms(1)
     raw = eng.tc_stats(False).astype(np.float64) / 1.9e3 / 312  # us per step
     names = ["EA", "sync", "B", "sync", "C", "sync", "D", "sync"]
-    for role, sl in (("lstm", slice(0, 128)), ("prenet", slice(128, 144))):
+    for role, sl in (("lstm", slice(0, 128)), ("prenet", slice(128, 144)), ("proj", slice(144, 148))):
         st = raw[sl, :8]
         print(f"B={B} {role:6s}: stage {ms:.2f} ms; us/step mean/max: " + " ".join(f"{n}={st[:, i].mean():.2f}/{st[:, i].max():.2f}" for i, n in enumerate(names)))
