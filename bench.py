@@ -343,7 +343,7 @@ def run_ours(args):
 
     # ---- callers of the path: duration model + one-call token->wav, chunked vocoding latency ----
     callers = None
-    if rank == 0:
+    if rank == 0 and not args.no_callers:
         eng.load_duration(synthetic.duration_ckpt(1234))
         for _ in range(2):
             waves, _ = eng.tts(tokens, silence_duration=0.05, seed=seed)
@@ -364,7 +364,22 @@ def run_ours(args):
         t0 = time.perf_counter()
         n_stream = sum(p.size for p in eng.mel2wave_stream(mel1, chunk_frames=32))
         all_ms = (time.perf_counter() - t0) * 1e3
+        # GTA forward (gta.py:28-41): int16 audio -> MelFilter -> teacher-forced acoustic model with zoneout
+        eng.load_mel_filterbank()
+        S_g = N * C.HOP
+        wav_i16 = (np.random.default_rng(1).standard_normal((B, S_g)) * 3000).astype(np.int16)
+        dur_sec = durs * np.float32(C.HOP / C.SAMPLE_RATE)
+        for _ in range(2):
+            eng.gta(wav_i16, tokens, dur_sec, seed=seed)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.gta(wav_i16, tokens, dur_sec, seed=seed)
+        dt_gta = (time.perf_counter() - t0) / reps
+        gta_dev_ms = eng.last_stage_ms(1)
         callers = dict(
+            gta=dict(api="vtts_gta_host (int16 audio -> log-mel -> shift -> teacher-forced acoustic model, zoneout + dropout on), host buffers",
+                     batch=B, frames_per_s=B * N / dt_gta, ms_per_call=dt_gta * 1e3, teacher_forced_model_ms=gta_dev_ms,
+                     autoregressive_model_ms=ac_ms),
             text_to_wav=dict(api="vtts_tts_host (duration model -> duration fix-ups -> acoustic -> trailing-silence trim -> generator), host buffers",
                              batch=B, samples_per_s=tts_samples / dt_tts, ms_per_call=dt_tts * 1e3, samples_per_call=tts_samples,
                              duration_model_ms=dur_ms),
@@ -430,6 +445,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--ref-rows", type=int, default=1, help="utterances per step of the CPU reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-callers", action="store_true", help="skip the duration/tts/gta/streaming side measurements (profiling runs)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"],
                     help="conv arithmetic: bf16x3 = tcgen05 split-bf16 with fp32 accumulate (default), fp32 = FMA pipe")
     args = ap.parse_args()

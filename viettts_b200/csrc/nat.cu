@@ -666,6 +666,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       if (t > 0) {
         dec_fetch(xs, XP, 0, a.h1 + (size_t)prv * B * H, H, H, B);
         __syncthreads();
+#pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
           pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB + H1OFF, part, outv);
           if (orow < B) {
@@ -684,7 +685,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       __syncthreads();
       dec_fetch(xs, XP, 0, a.p1, vc::PRENET, vc::PRENET, B);
       __syncthreads();
-      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
         pre_gemm8<4>(xs, XP, w2s + (size_t)hf * W2B, part, outv);
         if (orow < B) {
           const int u = q * 16 + hf * 8 + ocol;
@@ -701,7 +703,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       __syncthreads();
       dec_fetch(xs, XP, 0, a.h0 + (size_t)cur * B * H, H, H, B);
       __syncthreads();
-      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
         pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB, part, outv);
         pp1[hf * 256 + tid] = outv[tid];
       }
@@ -743,10 +746,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       // output frame t-1, off the critical path: h_{t-1} stays intact until phase C of frame t+1
       if (t > 0) { stage((t & 1) ^ 1); pass(t - 1, 0); }
       grid.sync();
-      if (t > 0) { pass(t - 1, 1); pass(t - 1, 2); }
+      if (t > 0) {
+#pragma unroll 1
+        for (int ps = 1; ps < 3; ++ps) pass(t - 1, ps);
+      }
       grid.sync();
     }
     stage((N - 1) & 1);
+#pragma unroll 1
     for (int ps = 0; ps < 3; ++ps) pass(N - 1, ps);
   }
 #undef DEC_MARK
