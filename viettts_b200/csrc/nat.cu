@@ -89,18 +89,6 @@ __global__ void repack_cols_kernel(const float* __restrict__ src, int ld, int ro
   }
 }
 
-// projection weights [1024][80] -> [4 CTAs][3 passes][1024 + 64 pad rows][8], already in the padded layout
-// pre_gemm8 reads (physical row = k + k/16); columns beyond the CTA's 20 are zero.
-__global__ void repack_proj_kernel(const float* __restrict__ src, float* __restrict__ dst) {
-  const int total = 4 * 3 * 1024 * 8;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int c8 = idx % 8, k = (idx / 8) % 1024, ps = (idx / (8 * 1024)) % 3, q = idx / (8 * 1024 * 3);
-    const int lc = ps * 8 + c8;
-    const float v = lc < 20 ? src[(size_t)k * vc::MEL + q * 20 + lc] : 0.f;
-    dst[(((size_t)q * 3 + ps) * (1024 + 64) + k + k / 16) * 8 + c8] = v;
-  }
-}
-
 // ---- Gaussian upsampling (model.py:102-111) --------------------------------------------------------
 // out[b,n,:] = sum_l softmax_l(-(mid_l - n)^2/10) enc[b,l,:],  mid = cumsum(dur) - dur/2
 constexpr int UP_F = 8;  // frames per CTA
@@ -207,7 +195,7 @@ struct EncScanArgs {
 };
 
 // ---- autoregressive decoder scan (model.py:129-142) ------------------------------------------------
-// One cooperative grid of 148 CTAs, up to 32 batch rows per launch.
+// One cooperative grid of 144 CTAs, up to 32 batch rows per launch.
 //   CTAs 0..127   LSTM role: CTA c owns 4 hidden units (16 gate columns) of both layers; its slices of the
 //                 recurrent matrices (768x16 + 1280x16 fp32) live in REGISTERS.  A persistent shared-memory
 //                 buffer holds [p2 | h0 | h1] of all rows; the parts that are already final (h0_{t-1},
@@ -215,8 +203,10 @@ struct EncScanArgs {
 //                 are fetched on the critical path.
 //   CTAs 128..143 prenet role: 16 columns each of p1 = drop(relu([h0,h1]_{t-1}.(Wo.W1) + bo.W1))  (phase EA)
 //                 and of p2 = drop(relu(p1.W2))                                                   (phase B)
-//   CTAs 144..147 projection role: 20 columns each of mel_{t-1} = [h0,h1]_{t-1}.Wo + bo, computed off the
-//                 critical path (during phase C of the next frame).
+// The output projection mel_t = [h0,h1]_t.Wo + bo is NOT part of the scan: nothing in the recurrence reads mel_t
+// (the prenet consumes the precomposed Wo.W1), so every frame's [h0 | h1] is written to `hout` and one GEMM
+// projects the whole sequence afterwards.  (A projection role inside the scan -- 4 CTAs taking part in every grid
+// barrier -- was the slowest arrival at the C and D barriers for small batches: 15 us per frame at B = 1.)
 // Four grid barriers per frame: EA | B | C (LSTM0) | D (LSTM1).
 struct DecScanArgs {
   const float* zc0;      // [B][N][2048] cond.W0[0:512] + b0
@@ -226,16 +216,15 @@ struct DecScanArgs {
   const float* wc;       // [16][1024][16]   (Wo . W1) columns, 16 per prenet CTA
   const float* bc;       // [256]            bo . W1
   const float* wp2;      // [16][256][16]    prenet fc2 columns
-  const float* wo;       // [4][3][1088][8]  projection columns in pre_gemm8 layout, 20 per projection CTA
-  const float* bo;       // [80]
   const uint8_t* keep;   // [B][N][2][256] or null (indexed with row_base)
   uint64_t seed;
   int mode;
   float* p1;             // [B][256]
   float* p2;             // [B][256]
-  float* h0;             // [2][B][512]
+  float* h0;             // [2][B][512] compact double-buffered state the recurrence reads (frame parity)
   float* h1;             // [2][B][512]
-  float* mel;            // [B][N][80]  (pre-postnet output)
+  float* hout;           // [B][N][1024] decoder outputs [h0_t | h1_t] of every frame (write only): the output projection
+                         // runs over the whole tensor as ONE GEMM after the scan
   int B, N;              // rows of this launch (<= 32), frames
   int row_base;          // first row of this launch inside the full batch (dropout stream indexing)
   int N_total_rows;      // unused
@@ -244,9 +233,8 @@ struct DecScanArgs {
 
 constexpr int DEC_XR = 32;                 // batch rows per launch
 constexpr int DEC_KPAD = vc::PRENET + 2 * vc::DEC_H + 4;   // 1284: [p2 | h0 | h1] + pad
-constexpr int DEC_CTAS = 148;
-constexpr int DEC_LSTM = 128, DEC_PRE = 16;   // + 4 projection CTAs = DEC_CTAS
-constexpr int PRE_KP = 2 * vc::DEC_H + 4;  // 1028: row pitch of the prenet CTAs' [h0 | h1] buffer
+constexpr int DEC_LSTM = 128, DEC_PRE = 16;
+constexpr int DEC_CTAS = DEC_LSTM + DEC_PRE;   // 144
 
 // copy rows [0,nr) x [n floats] of a global matrix (row stride `stride`) into smem (row pitch `pitch`, column
 // offset koff); p == nullptr writes zeros.  8 x 16 B loads in flight per thread.
@@ -593,11 +581,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
     __syncthreads();
     const int ngroups = (B + RG - 1) / RG;
     for (int t = 0; t < N; ++t) {
-      const int cur = t & 1, prv = cur ^ 1;
       // ---- EA window (prenet CTAs are busy): products of the state that is already final ----
       if (t > 0) {
         // h0_{t-1} is still resident in xs (fetched as h0_t in phase D of the previous frame); only h1_{t-1} is new
-        dec_fetch(xs, DEC_KPAD, vc::PRENET + H, a.h1 + (size_t)prv * B * H, H, H, B);
+        dec_fetch(xs, DEC_KPAD, vc::PRENET + H, a.h1 + (size_t)((t - 1) & 1) * B * H, H, H, B);
         dec_matmul<SLH>(xs + vc::PRENET, w0h, ngroups, part, zp0, nullptr);     // its barriers also order the h1 fetch
         dec_matmul<SLH>(xs + vc::PRENET + H, w1h1, ngroups, part, zp1, nullptr);
       }
@@ -617,13 +604,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
         float cc = cst[r * UPC + uu];
         const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
         cst[r * UPC + uu] = cc;
-        a.h0[((size_t)cur * B + r) * H + c * UPC + uu] = h;
+        a.h0[((size_t)(t & 1) * B + r) * H + c * UPC + uu] = h;
+        a.hout[((size_t)r * N + t) * 2 * H + c * UPC + uu] = h;
       }
       DEC_MARK(4)
       grid.sync();
       DEC_MARK(5)
       // ---- phase D: LSTM1 = zc1[t] + p2 . W1[p2 rows] + h0_t . W1[h0 rows] + (h1_{t-1} part) ----
-      dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)cur * B * H, H, H, B);
+      dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)(t & 1) * B * H, H, H, B);
       __syncthreads();
       dec_matmul2<SLP, SLH>(xs, w1p, xs + vc::PRENET, w1h0, ngroups, part, zs, zp1);
       if (tid < B * UPC) {
@@ -632,7 +620,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
         float cc = cst[(DEC_XR + r) * UPC + uu];
         const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
         cst[(DEC_XR + r) * UPC + uu] = cc;
-        a.h1[((size_t)cur * B + r) * H + c * UPC + uu] = h;
+        a.h1[((size_t)(t & 1) * B + r) * H + c * UPC + uu] = h;
+        a.hout[((size_t)r * N + t) * 2 * H + H + c * UPC + uu] = h;
       }
       __syncthreads();
       DEC_MARK(6)
@@ -661,10 +650,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
     const int orow = tid >> 3, ocol = tid & 7;         // output handled by this thread after a pre_gemm8 pass
     constexpr int H1OFF = (H + H / 8) * 8;             // first padded row of the h1 half inside a WCB block
     for (int t = 0; t < N; ++t) {
-      const int cur = t & 1, prv = cur ^ 1;
       // ---- phase EA: p1(t) = drop(relu(pp1 + h1_{t-1} . Wc[512:1024] + bc)) ----
       if (t > 0) {
-        dec_fetch(xs, XP, 0, a.h1 + (size_t)prv * B * H, H, H, B);
+        dec_fetch(xs, XP, 0, a.h1 + (size_t)((t - 1) & 1) * B * H, H, H, B);
         __syncthreads();
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
@@ -701,7 +689,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       DEC_MARK(5)
       // ---- D window: h0_t is final -> its half of p1(t+1)'s pre-activation ----
       __syncthreads();
-      dec_fetch(xs, XP, 0, a.h0 + (size_t)cur * B * H, H, H, B);
+      dec_fetch(xs, XP, 0, a.h0 + (size_t)(t & 1) * B * H, H, H, B);
       __syncthreads();
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
@@ -713,48 +701,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       grid.sync();
       DEC_MARK(7)
     }
-  } else {
-    // =============================== projection role ===============================
-    const int q = c - DEC_LSTM - DEC_PRE;              // mel columns 20q .. 20q+19 (3 passes of 8, last padded)
-    constexpr int WBLK = (2 * H + NSLICE) * 8;         // one pass of weights in pre_gemm8 layout
-    float* xs = sm;                                    // [32][PRE_KP]
-    float* wos = xs + 32 * PRE_KP;                     // passes 0 and 1 in smem; pass 2 (4 real columns) is read from L2/L1
-    float* part = wos + 2 * WBLK;                      // [8][32][8]
-    float* outv = part + 8 * 256;
-    const float* wg = a.wo + (size_t)q * 3 * WBLK;
-    for (int e = tid; e < 2 * WBLK / 4; e += SCAN_THREADS)
-      reinterpret_cast<float4*>(wos)[e] = __ldg(reinterpret_cast<const float4*>(wg) + e);
-    for (int e = tid; e < 32 * PRE_KP; e += SCAN_THREADS) xs[e] = 0.f;
-    __syncthreads();
-    const int orow = tid >> 3, ocol = tid & 7;
-    auto stage = [&](int buf) {
-      dec_fetch(xs, PRE_KP, 0, a.h0 + (size_t)buf * B * H, H, H, B);
-      dec_fetch(xs, PRE_KP, H, a.h1 + (size_t)buf * B * H, H, H, B);
-      __syncthreads();
-    };
-    auto pass = [&](int tf, int ps) {        // 8 columns of mel_{tf}
-      pre_gemm8<16>(xs, PRE_KP, ps < 2 ? wos + (size_t)ps * WBLK : wg + (size_t)2 * WBLK, part, outv);
-      const int lc = ps * 8 + ocol;
-      if (orow < B && lc < 20) {
-        const int m = q * 20 + lc;
-        a.mel[((size_t)orow * N + tf) * vc::MEL + m] = outv[tid] + __ldg(a.bo + m);
-      }
-    };
-    for (int t = 0; t < N; ++t) {
-      grid.sync();
-      grid.sync();
-      // output frame t-1, off the critical path: h_{t-1} stays intact until phase C of frame t+1
-      if (t > 0) { stage((t & 1) ^ 1); pass(t - 1, 0); }
-      grid.sync();
-      if (t > 0) {
-#pragma unroll 1
-        for (int ps = 1; ps < 3; ++ps) pass(t - 1, ps);
-      }
-      grid.sync();
-    }
-    stage((N - 1) & 1);
-#pragma unroll 1
-    for (int ps = 0; ps < 3; ++ps) pass(N - 1, ps);
   }
 #undef DEC_MARK
   if (a.dbg && tid == 0)
@@ -906,9 +852,7 @@ constexpr size_t enc_scan_smem() {
 constexpr size_t dec_scan_smem() {
   constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + 3 * DEC_XR * NCOL + 2 * DEC_XR * UPC;
   constexpr size_t pre = (size_t)32 * (vc::DEC_H + 4) + 2 * (2 * vc::DEC_H + 2 * vc::DEC_H / 8) * 8 + 2 * (vc::PRENET + NSLICE) * 8 + 8 * 256 + 256 + 512;
-  constexpr size_t proj = (size_t)32 * PRE_KP + 2 * (2 * vc::DEC_H + NSLICE) * 8 + 8 * 256 + 256;
-  constexpr size_t m1 = lstm > pre ? lstm : pre;
-  return (m1 > proj ? m1 : proj) * 4;
+  return (lstm > pre ? lstm : pre) * 4;
 }
 
 // derived-weight slots (ctx->ac_d)
@@ -922,7 +866,6 @@ enum {
   D_DEC_WCFULL,  // [1024][256] scratch
   D_DEC_BC,      // [256]
   D_DEC_WP2,     // [128][256][2]
-  D_DEC_WO,      // [4][3][1088][8] (20 columns used per CTA)
   D_ZERO,        // [2048] zeros: bias of the bias-free prenet linears (model.py:88-89) on the generic conv path
   D_COUNT
 };
@@ -988,7 +931,7 @@ static int run_token_encoder(vtts_ctx* ctx, const EncWeights& w, const int32_t* 
 int vtts_acoustic_prepare(vtts_ctx* ctx) {
   const size_t sizes[D_COUNT] = {256, 256, 256, 512, 512, 512, 512,
                                  (size_t)2 * 64 * 256 * 16, (size_t)128 * 768 * 16, (size_t)128 * 1280 * 16,
-                                 (size_t)16 * 1024 * 16, (size_t)1024 * 256, 256, (size_t)16 * 256 * 16, (size_t)4 * 3 * 1088 * 8, 2048};
+                                 (size_t)16 * 1024 * 16, (size_t)1024 * 256, 256, (size_t)16 * 256 * 16, 2048};
   size_t total = 0;
   std::vector<size_t> offs(D_COUNT);
   for (int i = 0; i < D_COUNT; ++i) {
@@ -1011,9 +954,7 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
   precompose_kernel<<<2 * vc::DEC_H + 1, 256>>>(T[aci::PROJ_W], T[aci::PROJ_B], T[aci::PRE1_W], ctx->ac_d[D_DEC_WCFULL], ctx->ac_d[D_DEC_BC]);
   repack_cols_kernel<<<256, 256>>>(ctx->ac_d[D_DEC_WCFULL], 256, 0, 1024, ctx->ac_d[D_DEC_WC], 16, 16, 16, 0);
   repack_cols_kernel<<<64, 256>>>(T[aci::PRE2_W], 256, 0, 256, ctx->ac_d[D_DEC_WP2], 16, 16, 16, 0);
-  VTTS_CUDA(cudaMemset(ctx->ac_d[D_DEC_WO], 0, (size_t)4 * 3 * 1088 * 8 * sizeof(float)));
   VTTS_CUDA(cudaMemset(ctx->ac_d[D_ZERO], 0, 2048 * sizeof(float)));
-  repack_proj_kernel<<<64, 256>>>(T[aci::PROJ_W], ctx->ac_d[D_DEC_WO]);
   VTTS_CUDA(cudaGetLastError());
   // ---- tensor-core packed weights of the convs and hoisted GEMMs ----
   {
@@ -1101,8 +1042,9 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   float* q1 = ar.take<float>(BN * 512);
   float* p1 = ar.take<float>((size_t)B * 256);
   float* p2 = ar.take<float>((size_t)B * 256);
-  float* h0 = ar.take<float>((size_t)2 * B * 512);
-  float* h1 = ar.take<float>((size_t)2 * B * 512);
+  float* hout = ar.take<float>(BN * 1024);
+  float* h0 = ar.take<float>((size_t)2 * DEC_XR * 512);
+  float* h1 = ar.take<float>((size_t)2 * DEC_XR * 512);
   if (measure) {
     *ws_need = ar.off + 256;
     return VTTS_OK;
@@ -1156,14 +1098,21 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     memset(&da, 0, sizeof(da));
     da.zc0 = zc0 + (size_t)b0 * N * 2048; da.zc1 = zc1 + (size_t)b0 * N * 2048;
     da.w0r = D[D_DEC_W0R]; da.w1r = D[D_DEC_W1R]; da.wc = D[D_DEC_WC]; da.bc = D[D_DEC_BC]; da.wp2 = D[D_DEC_WP2];
-    da.wo = D[D_DEC_WO]; da.bo = T[aci::PROJ_B];
     da.keep = keep; da.seed = seed; da.mode = mode;
-    da.p1 = p1; da.p2 = p2; da.h0 = h0; da.h1 = h1; da.mel = melpre + (size_t)b0 * N * 80;
+    da.p1 = p1; da.p2 = p2; da.h0 = h0; da.h1 = h1; da.hout = hout + (size_t)b0 * N * 1024;
     da.B = nb; da.N = N; da.row_base = b0; da.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
     void* args[] = {&da};
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(DEC_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
     ctx->launches++;
   }
+  // ---- output projection of every frame in one GEMM: mel_pre = [h0 | h1] . Wo + bo (model.py:135); fp32 FMA path in
+  //      both precision modes (1.6 GFLOP at B = 32); rows past n_frames[b] stay 0 ----
+  memset(&Lc, 0, sizeof(Lc));
+  Lc.nprob = 1; Lc.Cin = 1024; Lc.Cout = 80; Lc.B = B; Lc.T_rows = N; Lc.rows_out = N;
+  Lc.len = n_frames; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;
+  Lc.p[0] = ConvProb{hout, nullptr, nullptr, T[aci::PROJ_W], T[aci::PROJ_B], nullptr, nullptr, nullptr, nullptr, melpre, 1, 1, 0, 1, 0};
+  rc = vtts_launch_conv(ctx, Lc, st);
+  if (rc) return rc;
   rc = run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel, st);
   if (rc) return rc;
   return VTTS_OK;
