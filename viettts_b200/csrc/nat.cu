@@ -871,7 +871,7 @@ enum {
 };
 
 // slots of ctx->ac_wpk_t (tensor-core packed weights)
-enum { WP_ENC = 0, WP_ENCH = 3, WP_DECH = 11, WP_POST0 = 27, WP_POST1 = 29, WP_POST2 = 31, WP_POST3 = 33, WP_POST4 = 35, WP_COUNT = 36 };
+enum { WP_ENC = 0, WP_ENCH = 3, WP_DECH = 11, WP_POST0 = 27, WP_POST1 = 29, WP_POST2 = 31, WP_POST3 = 33, WP_POST4 = 35, WP_PROJ = 36, WP_COUNT = 37 };
 
 }  // namespace
 
@@ -960,7 +960,8 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
   {
     size_t bytes = 3 * vtts_tc_conv_packed_bytes(3, 256, 256) + 2 * vtts_tc_conv_packed_bytes(1, 256, 1024) +
                    2 * vtts_tc_conv_packed_bytes(1, 512, 2048) + vtts_tc_conv_packed_bytes(5, 80, 512) +
-                   3 * vtts_tc_conv_packed_bytes(5, 512, 512) + vtts_tc_conv_packed_bytes(5, 512, 80);
+                   3 * vtts_tc_conv_packed_bytes(5, 512, 512) + vtts_tc_conv_packed_bytes(5, 512, 80) +
+                   vtts_tc_conv_packed_bytes(1, 1024, 80);
     if (ctx->ac_wpk) cudaFree(ctx->ac_wpk);
     VTTS_CUDA(cudaMalloc(&ctx->ac_wpk, bytes));
     char* cur = (char*)ctx->ac_wpk;
@@ -974,6 +975,7 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
     if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(0, 0)], 5, 80, 512, cur, ctx->ac_wpk_t);
     for (int i = 1; i < 4 && !rc; ++i) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(i, 0)], 5, 512, 512, cur, ctx->ac_wpk_t);
     if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(4, 0)], 5, 512, 80, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::PROJ_W], 1, 1024, 80, cur, ctx->ac_wpk_t);
     if (rc) return rc;
     if ((int)ctx->ac_wpk_t.size() != WP_COUNT || (size_t)(cur - (char*)ctx->ac_wpk) > bytes)
       return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: packed weight table has %d entries", (int)ctx->ac_wpk_t.size());
@@ -1105,13 +1107,13 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(DEC_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
     ctx->launches++;
   }
-  // ---- output projection of every frame in one GEMM: mel_pre = [h0 | h1] . Wo + bo (model.py:135); fp32 FMA path in
-  //      both precision modes (1.6 GFLOP at B = 32); rows past n_frames[b] stay 0 ----
+  // ---- output projection of every frame in one GEMM: mel_pre = [h0 | h1] . Wo + bo (model.py:135);
+  //      rows past n_frames[b] stay 0 ----
   memset(&Lc, 0, sizeof(Lc));
   Lc.nprob = 1; Lc.Cin = 1024; Lc.Cout = 80; Lc.B = B; Lc.T_rows = N; Lc.rows_out = N;
   Lc.len = n_frames; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;
   Lc.p[0] = ConvProb{hout, nullptr, nullptr, T[aci::PROJ_W], T[aci::PROJ_B], nullptr, nullptr, nullptr, nullptr, melpre, 1, 1, 0, 1, 0};
-  rc = vtts_launch_conv(ctx, Lc, st);
+  rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_PROJ], st);
   if (rc) return rc;
   rc = run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel, st);
   if (rc) return rc;
