@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   // every role walks the same tile sequence
 #define TILE_LOOP_BEGIN                                                        \
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {              \
-    const int pi = tile / tiles_per_prob;      /* problems are laid out back to back, most expensive first */ \
-    const int rest = tile - pi * tiles_per_prob;                               \
+    const int pi = L.problem_major ? tile / tiles_per_prob : tile % L.nprob;    \
+    const int rest = L.problem_major ? tile - pi * tiles_per_prob : tile / L.nprob; \
     const int tt = rest % tiles_per_row;                                       \
     const int b = rest / tiles_per_row;                                        \
     const int tau0 = tt * R;                                                   \
@@ -579,6 +579,11 @@ int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
     if (L.p[i].k < 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: k");
   L.err = ctx->d_err;
   L.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
+  {
+    static int pm_env = -1;    // experiment switch: VTTS_TC_PROBLEM_MAJOR=0/1 forces the tile map of every launch
+    if (pm_env < 0) { const char* e = getenv("VTTS_TC_PROBLEM_MAJOR"); pm_env = e ? atoi(e) + 1 : 0; }
+    if (pm_env > 0) L.problem_major = pm_env - 1;
+  }
   switch (L.N) {
     case 256: return launch_n<256>(ctx, L, st);
     case 128: return launch_n<128>(ctx, L, st);

@@ -105,6 +105,10 @@ struct TcLaunch {
   int post_act;          // 0 none, 1 tanh, 2 relu (after BN, before the residual)
   int n_valid;           // real output channels of this N tile (<= N); 0 means N
   int tiles_per_row, ntiles;  // filled by the launcher
+  int problem_major;          // tile -> problem map.  0 (default): round robin (problem = tile % nprob): row tile r of every problem
+                              // is in flight at the same time, so an input / residual tensor the problems SHARE (the first pair
+                              // of every ResBlock stage, the ConvTranspose phases) is read from DRAM once and served from L2 to
+                              // the others: generator 19.8 -> 19.1 ms.  1: problems back to back (experiments only)
   int* err;                   // device int: set before trapping on a barrier timeout
   long long* dbg;             // optional [grid][16] per-role stall counters (vtts_debug_tc_stats)
 };
