@@ -343,7 +343,7 @@ def run_ours(args):
 
     # ---- callers of the path: duration model + one-call token->wav, chunked vocoding latency ----
     callers = None
-    if rank == 0 and not args.no_callers:
+    if rank == 0 and world == 1 and not args.no_callers:     # side measurements at N=1 only, like cpu_baseline
         eng.load_duration(synthetic.duration_ckpt(1234))
         for _ in range(2):
             waves, _ = eng.tts(tokens, silence_duration=0.05, seed=seed)
