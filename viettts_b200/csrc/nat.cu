@@ -223,6 +223,8 @@ struct DecScanArgs {
   float* p2;             // [B][256]
   float* h0;             // [2][B][512] compact double-buffered state the recurrence reads (frame parity)
   float* h1;             // [2][B][512]
+  unsigned int* pre_bar; // arrival counter of the prenet CTAs' private barrier (zeroed before the launch)
+  int* err;              // device int set before trapping on a barrier time-out
   float* hout;           // [B][N][1024] decoder outputs [h0_t | h1_t] of every frame (write only): the output projection
                          // runs over the whole tensor as ONE GEMM after the scan
   int B, N;              // rows of this launch (<= 32), frames
@@ -536,6 +538,29 @@ __device__ __forceinline__ void pre_load_w8(float* wsm, const float* g, int K, i
   }
 }
 
+// Barrier among the DEC_PRE prenet CTAs only (all co-resident: cooperative launch).  The second prenet layer needs every
+// column block of p1 from its 15 peers but nothing from the 128 LSTM CTAs, so a grid-wide barrier here would put the
+// LSTM CTAs' pre-accumulation (6.2 us at 32 rows) on the critical path and cost a full grid.sync.  `target` is the
+// monotonically growing arrival count; a 2 s time-out traps instead of hanging the GPU.
+__device__ __forceinline__ void prenet_barrier(unsigned int* counter, unsigned int target, int* err) {
+  __syncthreads();                                   // this CTA's p1 stores are issued
+  if (threadIdx.x == 0) {
+    __threadfence();                                 // ... and visible device-wide before the arrival is
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v < target && clock64() - t0 > 4000000000LL) {
+        if (err) *err = 77;
+        __threadfence_system();
+        asm volatile("trap;");
+      }
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const DecScanArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float sm[];
@@ -589,10 +614,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
         dec_matmul<SLH>(xs + vc::PRENET + H, w1h1, ngroups, part, zp1, nullptr);
       }
       DEC_MARK(0)
-      grid.sync();
       DEC_MARK(1)
       DEC_MARK(2)
-      grid.sync();
+      grid.sync();   // p2(t) is ready (the prenet CTAs order their two layers among themselves, see prenet_barrier)
       DEC_MARK(3)
       // ---- phase C: LSTM0 = zc0[t] + p2 . W0[p2 rows] + (h0_{t-1} part) ----
       dec_fetch(xs, DEC_KPAD, 0, a.p2, vc::PRENET, vc::PRENET, B);
@@ -667,10 +691,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
         for (int e = tid; e < B * 16; e += SCAN_THREADS) a.p1[(size_t)(e >> 4) * vc::PRENET + q * 16 + (e & 15)] = 0.f;  // prenet(0) = 0
       }
       DEC_MARK(0)
-      grid.sync();
+      prenet_barrier(a.pre_bar, (unsigned)DEC_PRE * (unsigned)(t + 1), a.err);   // every column block of p1(t) is in L2
       DEC_MARK(1)
       // ---- phase B: p2(t) = drop(relu(p1 . W2)) ----
-      __syncthreads();
       dec_fetch(xs, XP, 0, a.p1, vc::PRENET, vc::PRENET, B);
       __syncthreads();
 #pragma unroll 1
@@ -1047,6 +1070,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   float* hout = ar.take<float>(BN * 1024);
   float* h0 = ar.take<float>((size_t)2 * DEC_XR * 512);
   float* h1 = ar.take<float>((size_t)2 * DEC_XR * 512);
+  unsigned int* pre_bar = ar.take<unsigned int>(64);
   if (measure) {
     *ws_need = ar.off + 256;
     return VTTS_OK;
@@ -1102,6 +1126,8 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     da.w0r = D[D_DEC_W0R]; da.w1r = D[D_DEC_W1R]; da.wc = D[D_DEC_WC]; da.bc = D[D_DEC_BC]; da.wp2 = D[D_DEC_WP2];
     da.keep = keep; da.seed = seed; da.mode = mode;
     da.p1 = p1; da.p2 = p2; da.h0 = h0; da.h1 = h1; da.hout = hout + (size_t)b0 * N * 1024;
+    da.pre_bar = pre_bar; da.err = ctx->d_err;
+    VTTS_CUDA(cudaMemsetAsync(pre_bar, 0, sizeof(unsigned int), st));
     da.B = nb; da.N = N; da.row_base = b0; da.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
     void* args[] = {&da};
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(DEC_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
