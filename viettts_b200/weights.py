@@ -36,11 +36,36 @@ class _Opaque:
 
 
 def _np_from_jax(*args, **kwargs):
-    # jax arrays pickle as (reconstruct_fn, (numpy_array_or_args...)); keep the ndarray we find
+    """Stand-in for jax's array reconstruction functions.  Two pickled layouts exist:
+      * `reconstruct(fun, args, arr_state, aval_state)` (jax.Array / DeviceArray.__reduce__ since jax 0.2.10):
+        `fun, args, arr_state` are the numpy array's own `__reduce__` triple -> rebuild the ndarray from them;
+      * an ndarray passed directly (or a plain numpy pickle, which never reaches this function)."""
+    if len(args) >= 3 and callable(args[0]) and isinstance(args[1], tuple):
+        try:
+            arr = args[0](*args[1])
+            arr.__setstate__(args[2])
+            return np.asarray(arr)
+        except Exception:
+            pass
     for a in list(args) + list(kwargs.values()):
         if isinstance(a, np.ndarray):
             return a
     return _Opaque(*args, **kwargs)
+
+
+class _FlatMapping(dict):
+    """Stand-in for haiku's FlatMapping (hk.Params / hk.State).  Haiku pickles it as `FlatMapping(dict)`
+    (its `__reduce__` goes through a plain dict); very old versions used the default object protocol with the
+    mapping in `_mapping`.  Both restore to a plain dict of dicts."""
+
+    def __setstate__(self, state):
+        if isinstance(state, tuple) and len(state) == 2 and isinstance(state[0], dict):   # (dict_state, slots)
+            state = state[0]
+        m = state.get("_mapping") if isinstance(state, dict) else None
+        if m is None:
+            raise pickle.UnpicklingError("FlatMapping pickled as (treedef, leaves): re-save the checkpoint with "
+                                         "hk.data_structures.to_mutable_dict / jax.device_get, or load it once with haiku installed")
+        self.update(m)
 
 
 class _Unpickler(pickle.Unpickler):
@@ -49,19 +74,26 @@ class _Unpickler(pickle.Unpickler):
         if top in ("jax", "jaxlib"):
             return _np_from_jax
         if top == "haiku" or module.startswith("haiku."):
-            if "FlatMap" in name or "FlatMapping" in name:
-                return lambda *a, **k: dict(*a, **k)
+            if "FlatMap" in name:
+                return _FlatMapping
             return _Opaque
         if top in ("optax", "chex", "flax"):
             return _Opaque
         return super().find_class(module, name)
 
 
+def _plain(x):
+    """_FlatMapping -> dict, recursively (pack_* index plain dicts)."""
+    if isinstance(x, dict):
+        return {k: _plain(v) for k, v in x.items()}
+    return x
+
+
 def load_pickle(path):
     with open(path, "rb") as f:
         data = f.read()
     try:
-        return _Unpickler(io.BytesIO(data)).load()
+        return _plain(_Unpickler(io.BytesIO(data)).load())
     except Exception:
         return pickle.loads(data)
 
