@@ -81,3 +81,23 @@ def test_wav_roundtrip(tmp_path):
     import wave
     with wave.open(str(fn)) as f:   # an independent parser agrees on the header
         assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 16000, w.size)
+
+
+def test_pinned_buffers_are_released_with_the_array(monkeypatch):
+    """Engine.pinned_empty keeps the owning tensor alive only as long as the numpy array (or a view of it) lives."""
+    import gc
+    import torch
+    from viettts_b200.engine import Engine
+    real = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **k: real(*a, **k))   # no CUDA here: unpinned stand-in
+    n0 = len(Engine._pinned_keepalive)
+    a = Engine.pinned_empty((4, 8))
+    view = a[1:]
+    assert a.shape == (4, 8) and a.dtype == np.float32 and len(Engine._pinned_keepalive) == n0 + 1
+    del a
+    gc.collect()
+    assert len(Engine._pinned_keepalive) == n0 + 1      # the view still references the buffer
+    view[:] = 1.0
+    del view
+    gc.collect()
+    assert len(Engine._pinned_keepalive) == n0

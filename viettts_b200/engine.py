@@ -252,11 +252,15 @@ class Engine:
     @staticmethod
     def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
         """numpy array backed by page-locked host memory.  Passed as `out=` to synthesize / mel2wave the
-        library copies D2H straight into it (no staging copy, no page faults of a fresh array)."""
+        library copies D2H straight into it (no staging copy, no page faults of a fresh array).
+        The pinned allocation lives exactly as long as the array (or any view of it)."""
+        import weakref
         import torch
         t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
         a = t.numpy()
-        Engine._pinned_keepalive[a.ctypes.data] = t   # the tensor owns the memory
+        key = a.ctypes.data
+        Engine._pinned_keepalive[key] = t            # the tensor owns the memory ...
+        weakref.finalize(a, Engine._pinned_keepalive.pop, key, None)   # ... and is dropped with the array
         return a
 
     _pinned_keepalive: dict = {}
