@@ -146,6 +146,14 @@ int vtts_debug_pair(vtts_ctx* ctx, const float* x_dev, const float* w1_dev, cons
  * synchronises, copies (if host_out != NULL) and clears the counters. */
 int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16);
 
+/* profiling aid: per-kernel-group times of the LAST forward calls.  enable != 0 switches the event recording on for later
+ * calls.  ms_out24 (may be NULL) receives, for every id with both marks recorded, the elapsed ms since the previous
+ * id of the same group (0 otherwise); the call synchronises the device.  ids:
+ *   acoustic: 1 TokenEncoder, 2 upsample, 3 hoisted cond GEMMs, 4 decoder scan, 5 output projection, 6 postnet
+ *   hifigan:  9 conv_pre, 10..13 up-sampling stage 0..3 (ConvTranspose + three ResBlocks), 14 conv_post
+ *   teacher-forced pass: 17 encoder + upsample, 18 prenet + hoisted GEMMs, 19 zoneout scan, 20 projection + postnet */
+int vtts_debug_substages(vtts_ctx* ctx, int enable, float* ms_out24);
+
 /* ---- host-buffer entry points (what a ctypes / cgo / JNI binding calls) ------------------ */
 int vtts_mel2wave_host(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, int B, int T, float* wav);
 int vtts_predict_mel_host(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengths,

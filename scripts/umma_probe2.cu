@@ -19,7 +19,7 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
                ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-struct Args { int N; int iters; int variant; long long* out; };
+struct Args { int N; int iters; int variant; long long* out; int nwarps; };
 
 // variant: 0 SS triples, distinct A windows per M tile (production)      1 TS triples
 //          2 SS, no collector hints                                      3 SS, every MMA the SAME A and B descriptor
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128, 1) probe2(const Args a) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   for (int i = tid; i < (SMEM_BYTES - 2048) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(&bar, a.nwarps); mbar_init(&bar2, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(128, 1) probe2(const Args a) {
   const uint64_t a_tmpl = make_desc(0, 1024 * 16, 128);
   const uint64_t b_tmpl = make_desc(0, 256 * 16, 128);
   long long t_role = 0;
-  if (warp == 0) {
-    if (a.variant == 4 && lane == 0) mbar_arrive(&bar2);    // phase 0 complete: try_wait(parity 0) returns true immediately
+  if (warp < a.nwarps) {
+    if (a.variant == 4 && lane == 0 && warp == 0) mbar_arrive(&bar2);    // phase 0 complete: try_wait(parity 0) returns true immediately
     __syncwarp();
     const long long t0 = clock64();
     long long dummy = 0;
@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(128, 1) probe2(const Args a) {
       if (elect_one()) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d = tmem_base + (uint32_t)mt * (uint32_t)(N < 32 ? 32 : N) % 256u;
+          const uint32_t d = tmem_base + (uint32_t)((warp * MT + mt) * (N < 32 ? 32 : N)) % 256u;
           if (a.variant == 1) {
-            const uint32_t slot = tmem_base + 256 + (uint32_t)((it + mt) & 7) * 16;
+            const uint32_t slot = tmem_base + 256 + (uint32_t)((it + mt + warp * 2) & 7) * 16;
             umma_ts(d, slot, bd0, idesc, 1u);
             umma_ts(d, slot, bd1, idesc, 1u);
             umma_ts(d, slot + 8, bd0, idesc, 1u);
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(128, 1) probe2(const Args a) {
             const uint64_t bd = b_tmpl | (uint64_t)b16;
             umma<0>(d, ad, bd, idesc, 1u); umma<0>(d, ad, bd, idesc, 1u); umma<0>(d, ad, bd, idesc, 1u);
           } else {
-            const uint64_t ad_hi = a_tmpl | (uint64_t)(aoff + mt * 128);
-            const uint64_t ad_lo = a_tmpl | (uint64_t)(aoff + mt * 128 + 2048);
+            const uint64_t ad_hi = a_tmpl | (uint64_t)(aoff + (mt + warp * MT) % 6 * 128);
+            const uint64_t ad_lo = a_tmpl | (uint64_t)(aoff + (mt + warp * MT) % 6 * 128 + 2048);
             if (a.variant == 2) {
               umma<0>(d, ad_hi, bd0, idesc, 1u); umma<0>(d, ad_hi, bd1, idesc, 1u); umma<0>(d, ad_lo, bd0, idesc, 1u);
             } else {
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128, 1) probe2(const Args a) {
     long long acc = 0;
     mbar_wait_t(&bar, 0, nullptr, 0, acc);
     t_role = clock64() - t0;
-    if (lane == 0) a.out[blockIdx.x] = t_role + (dummy & 0);
+    if (lane == 0 && warp == 0) a.out[blockIdx.x] = t_role + (dummy & 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(128, 1) probe2(const Args a) {
 }
 
 template <int MT>
-static double run(int N, int variant, int iters, long long* d_out) {
+static double run(int N, int variant, int iters, long long* d_out, int nwarps = 1) {
   static bool attr = false;
   if (!attr) { CK(cudaFuncSetAttribute(probe2<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-  Args a{N, iters, variant, d_out};
+  Args a{N, iters, variant, d_out, nwarps};
   probe2<MT><<<148, 128, SMEM_BYTES>>>(a);
   CK(cudaDeviceSynchronize());
   static long long h[148];
@@ -129,6 +129,16 @@ int main() {
       const double c1 = run<1>(N, v, iters, d_out), c2 = run<2>(N, v, iters, d_out), c4 = run<4>(N, v, iters, d_out), c8 = run<8>(N, v, iters, d_out);
       printf("  N=%3d  MT=1 %7.1f  MT=2 %7.1f  MT=4 %7.1f  MT=8 %7.1f   -> per-MMA slope (MT 4->8) %.1f clk, math floor %d clk/MMA\n", N, c1, c2, c4,
              c8, (c8 - c4) / 12.0, N / 2);
+    }
+  }
+  printf("\n[6] several issuing warps at once (each its own accumulators), clk per region-set and aggregate clk per MMA\n");
+  for (int v : {0, 1}) {
+    printf("  %s\n", names[v]);
+    for (int N : {32, 64}) {
+      for (int W : {1, 2, 4}) {
+        const double c1 = run<1>(N, v, iters, d_out, W), c2 = run<2>(N, v, iters, d_out, W);
+        printf("    N=%3d warps=%d  MT=1: %7.1f (%5.1f /MMA)  MT=2: %7.1f (%5.1f /MMA)\n", N, W, c1, c1 / (3.0 * W), c2, c2 / (6.0 * W));
+      }
     }
   }
   return 0;

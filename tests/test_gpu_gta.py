@@ -148,5 +148,11 @@ def test_gta_dropin_writes_reference_format(eng, acoustic_ckpt, tmp_path, monkey
     files = gta.generate_gta([(["a", "b"], wav, wl, tok, np.array([L, L], np.int32), dur)], tmp_path / "gta", keep_masks=keep, zone_masks=zone)
     a, b = np.load(files[0]), np.load(files[1])
     assert a.shape == (80, 30) and b.shape == (80, 21) and a.dtype == np.float32
-    ref = eng.gta(wav, tok, dur, lengths=[L, L], wav_lengths=wl, keep_masks=keep, zone_masks=zone)
+    # like the reference's forward_fn_ (gta.py:28-41) the model runs over the FULL padded length; wav_lengths only
+    # slices the saved array (gta.py:70-76)
+    ref = eng.gta(wav, tok, dur, lengths=[L, L], wav_lengths=None, keep_masks=keep, zone_masks=zone)
     assert np.array_equal(a, ref[0].T) and np.array_equal(b, ref[1, :21].T)
+    # and the saved short row equals the oracle's forward over the full padded N, sliced (the last ~10 frames before
+    # the cut see postnet context from frames >= l, exactly as in the reference)
+    _, mel2 = no.gta_forward(acoustic_ckpt, wav, tok, np.array([L, L]), dur, keep, zone, dtype=torch.float64)
+    assert np.abs(b - mel2[1, :21].T).max() < 2 * MEL_LINF

@@ -282,6 +282,22 @@ int vtts_set_precision(vtts_ctx* ctx, int mode) {
 
 int vtts_get_precision(vtts_ctx* ctx) { return ctx ? ctx->precision : VTTS_ERR_BAD_ARG; }
 
+int vtts_debug_substages(vtts_ctx* ctx, int enable, float* ms_out24) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  VTTS_CUDA(cudaDeviceSynchronize());
+  if (ms_out24) {
+    for (int i = 0; i < vtts_ctx::NSUB; ++i) {
+      ms_out24[i] = 0.f;
+      if ((i % 8) == 0 || !ctx->sub_set[i] || !ctx->sub_set[i - 1]) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->sub_ev[i - 1], ctx->sub_ev[i]) == cudaSuccess) ms_out24[i] = ms;
+    }
+  }
+  for (int i = 0; i < vtts_ctx::NSUB; ++i) ctx->sub_set[i] = false;
+  ctx->sub_on = enable != 0;
+  return VTTS_OK;
+}
+
 int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16) {
   if (!ctx) return VTTS_ERR_BAD_ARG;
   VTTS_CUDA(cudaSetDevice(ctx->device));

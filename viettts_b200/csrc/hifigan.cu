@@ -203,6 +203,7 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
   L.B = B;
   L.len = n_frames;
 
+  ctx->sub_mark(8, st);
   // conv_pre: 80 -> 512, k7 pad 3
   L.nprob = 1;
   L.Cin = vc::MEL; L.Cout = vc::HG_C0;
@@ -222,6 +223,7 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
     rc = vtts_launch_conv(ctx, L, st);
   }
   if (rc) return rc;
+  ctx->sub_mark(9, st);
 
   int C = vc::HG_C0;      // input channels of the stage
   int rows_in = T;        // rows per batch item entering the stage
@@ -362,6 +364,7 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
     C = Co;
     rows_in = rows;
     scale_in = scale;
+    ctx->sub_mark(10 + i, st);
   }
   // ---- mean of 3, lrelu(0.01), conv_post (32 -> 1, k7), tanh ----
   {
@@ -371,5 +374,6 @@ int vtts_hifigan_run(vtts_ctx* ctx, const float* mel, const int32_t* n_frames, i
     ctx->launches++;
     VTTS_CUDA(cudaGetLastError());
   }
+  ctx->sub_mark(14, st);
   return VTTS_OK;
 }

@@ -56,7 +56,10 @@ __device__ __forceinline__ float keep_scale(int mode, const uint8_t* keep, uint6
   if (mode == VTTS_DROPOUT_OFF) return 1.f;
   if (mode == VTTS_DROPOUT_MASK) return keep[(((size_t)b * N + t) * 2 + layer) * vc::PRENET + unit] ? 2.f : 0.f;
   uint32_t o0, o1;
-  threefry2x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(b * (uint32_t)N + t), (uint32_t)(layer * vc::PRENET + unit), o0, o1);
+  // counter = (frame, row << 12 | entry): a row's stream depends on its row index in the call and the absolute frame,
+  // not on the padded frame count N of the batch it happens to share
+  (void)N;
+  threefry2x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)t, ((uint32_t)b << 12) | (uint32_t)(layer * vc::PRENET + unit), o0, o1);
   return (o0 < 0x80000000u) ? 2.f : 0.f;
 }
 
@@ -774,7 +777,8 @@ __device__ __forceinline__ bool zone_keep(int mode, const uint8_t* zone, uint64_
   if (mode == VTTS_DROPOUT_OFF) return false;
   if (mode == VTTS_DROPOUT_MASK) return zone[(((size_t)b * N + t) * 4 + which) * vc::DEC_H + unit] != 0;
   uint32_t o0, o1;
-  threefry2x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(b * (uint32_t)N + t), (uint32_t)(2 * vc::PRENET + which * vc::DEC_H + unit), o0, o1);
+  (void)N;
+  threefry2x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)t, ((uint32_t)b << 12) | (uint32_t)(2 * vc::PRENET + which * vc::DEC_H + unit), o0, o1);
   return o0 < 429496730u;   // 0.1 * 2^32
 }
 
@@ -894,7 +898,9 @@ enum {
 };
 
 // slots of ctx->ac_wpk_t (tensor-core packed weights)
-enum { WP_ENC = 0, WP_ENCH = 3, WP_DECH = 11, WP_POST0 = 27, WP_POST1 = 29, WP_POST2 = 31, WP_POST3 = 33, WP_POST4 = 35, WP_PROJ = 36, WP_COUNT = 37 };
+enum { WP_ENC = 0, WP_ENCH = 3, WP_DECH = 11, WP_POST0 = 27, WP_POST1 = 29, WP_POST2 = 31, WP_POST3 = 33, WP_POST4 = 35, WP_PROJ = 36,
+       // teacher-forced pass: [cond | p2] rows 0..767 of both decoder LSTMs (8 N=256 tiles each), the two prenet linears
+       WP_TF_L0 = 37, WP_TF_L1 = 45, WP_PRE1 = 53, WP_PRE2 = 54, WP_COUNT = 55 };
 
 }  // namespace
 
@@ -984,7 +990,8 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
     size_t bytes = 3 * vtts_tc_conv_packed_bytes(3, 256, 256) + 2 * vtts_tc_conv_packed_bytes(1, 256, 1024) +
                    2 * vtts_tc_conv_packed_bytes(1, 512, 2048) + vtts_tc_conv_packed_bytes(5, 80, 512) +
                    3 * vtts_tc_conv_packed_bytes(5, 512, 512) + vtts_tc_conv_packed_bytes(5, 512, 80) +
-                   vtts_tc_conv_packed_bytes(1, 1024, 80);
+                   vtts_tc_conv_packed_bytes(1, 1024, 80) + 2 * vtts_tc_conv_packed_bytes(1, 768, 2048) +
+                   vtts_tc_conv_packed_bytes(1, 80, 256) + vtts_tc_conv_packed_bytes(1, 256, 256);
     if (ctx->ac_wpk) cudaFree(ctx->ac_wpk);
     VTTS_CUDA(cudaMalloc(&ctx->ac_wpk, bytes));
     char* cur = (char*)ctx->ac_wpk;
@@ -999,6 +1006,10 @@ int vtts_acoustic_prepare(vtts_ctx* ctx) {
     for (int i = 1; i < 4 && !rc; ++i) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(i, 0)], 5, 512, 512, cur, ctx->ac_wpk_t);
     if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::POST_CONV(4, 0)], 5, 512, 80, cur, ctx->ac_wpk_t);
     if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::PROJ_W], 1, 1024, 80, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::DEC_L0_W], 1, 768, 2048, cur, ctx->ac_wpk_t);   // rows 0..767 = [cond | p2]
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::DEC_L1_W], 1, 768, 2048, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::PRE1_W], 1, 80, 256, cur, ctx->ac_wpk_t);
+    if (!rc) rc = vtts_tc_pack_conv(ctx, T[aci::PRE2_W], 1, 256, 256, cur, ctx->ac_wpk_t);
     if (rc) return rc;
     if ((int)ctx->ac_wpk_t.size() != WP_COUNT || (size_t)(cur - (char*)ctx->ac_wpk) > bytes)
       return ctx->fail(VTTS_ERR_BAD_ARG, "acoustic: packed weight table has %d entries", (int)ctx->ac_wpk_t.size());
@@ -1084,6 +1095,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   VTTS_CUDA(cudaMemsetAsync(mel, 0, BN * 80 * sizeof(float), st));
   VTTS_CUDA(cudaMemsetAsync(cond, 0, BN * 512 * sizeof(float), st));
   VTTS_CUDA(cudaMemsetAsync(melpre, 0, BN * 80 * sizeof(float), st));
+  ctx->sub_mark(0, st);
 
   // ---- TokenEncoder (shared with the duration model, run_token_encoder above) ----
   {
@@ -1098,6 +1110,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     int rc = run_token_encoder(ctx, ew, tokens, lengths, B, L, e0, e1, zx, enc, st);
     if (rc) return rc;
   }
+  ctx->sub_mark(1, st);
   // ---- Gaussian upsampling ----
   {
     dim3 grid((N + UP_F - 1) / UP_F, B);
@@ -1108,6 +1121,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     ctx->launches++;
     VTTS_CUDA(cudaGetLastError());
   }
+  ctx->sub_mark(2, st);
   // ---- hoisted cond projections of the decoder LSTMs ----
   ConvLaunch Lc;
   memset(&Lc, 0, sizeof(Lc));
@@ -1117,6 +1131,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   Lc.p[1] = ConvProb{cond, nullptr, nullptr, T[aci::DEC_L1_W], T[aci::DEC_L1_B], nullptr, nullptr, nullptr, nullptr, zc1, 1, 1, 0, 1, 0};
   int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_DECH], st);
   if (rc) return rc;
+  ctx->sub_mark(3, st);
   // ---- autoregressive scan: launches of up to 32 rows (rows are independent) ----
   for (int b0 = 0; b0 < B; b0 += DEC_XR) {
     const int nb = B - b0 < DEC_XR ? B - b0 : DEC_XR;
@@ -1133,6 +1148,7 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_scan_kernel, dim3(DEC_CTAS), dim3(SCAN_THREADS), args, dec_scan_smem(), st));
     ctx->launches++;
   }
+  ctx->sub_mark(4, st);
   // ---- output projection of every frame in one GEMM: mel_pre = [h0 | h1] . Wo + bo (model.py:135);
   //      rows past n_frames[b] stay 0 ----
   memset(&Lc, 0, sizeof(Lc));
@@ -1141,8 +1157,10 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   Lc.p[0] = ConvProb{hout, nullptr, nullptr, T[aci::PROJ_W], T[aci::PROJ_B], nullptr, nullptr, nullptr, nullptr, melpre, 1, 1, 0, 1, 0};
   rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_PROJ], st);
   if (rc) return rc;
+  ctx->sub_mark(5, st);
   rc = run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel, st);
   if (rc) return rc;
+  ctx->sub_mark(6, st);
   return VTTS_OK;
 }
 
@@ -1194,6 +1212,7 @@ int vtts_acoustic_teacher_run(vtts_ctx* ctx, const int32_t* tokens, const int32_
   if (mel1) VTTS_CUDA(cudaMemsetAsync(mel1, 0, BN * 80 * sizeof(float), st));
   VTTS_CUDA(cudaMemsetAsync(xin, 0, BN * XW * sizeof(float), st));
   VTTS_CUDA(cudaMemsetAsync(melpre, 0, BN * 80 * sizeof(float), st));
+  ctx->sub_mark(16, st);
   {
     EncWeights ew;
     ew.embed = T[aci::EMBED];
@@ -1215,22 +1234,23 @@ int vtts_acoustic_teacher_run(vtts_ctx* ctx, const int32_t* tokens, const int32_
     ctx->launches++;
     VTTS_CUDA(cudaGetLastError());
   }
+  ctx->sub_mark(17, st);
   // ---- prenet over the whole sequence (model.py:95-100,149): two bias-free linears, relu, dropout 0.5 each ----
   ConvLaunch Lc;
-  auto gemm = [&](const float* x, const float* w, const float* bias, float* out, int cin, int cout) {
+  auto gemm = [&](const float* x, const float* w, const float* bias, float* out, int cin, int cout, int wp) {
     memset(&Lc, 0, sizeof(Lc));
     Lc.nprob = 1; Lc.Cin = cin; Lc.Cout = cout; Lc.B = 1; Lc.T_rows = (int)BN; Lc.rows_out = (int)BN;
     Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0; Lc.len_mul = 1;
     Lc.p[0] = ConvProb{x, nullptr, nullptr, w, bias, nullptr, nullptr, nullptr, nullptr, out, 1, 1, 0, 1, 0};
-    return vtts_launch_conv(ctx, Lc, st);
+    return vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[wp], st);     // tensor-core path in BF16X3 mode, FMA path in FP32 mode
   };
   const size_t act_blocks = (BN * 256 + 255) / 256;
   const unsigned act_grid = (unsigned)(act_blocks < 148 * 16 ? act_blocks : 148 * 16);
-  int rc = gemm(mels_in, T[aci::PRE1_W], D[D_ZERO], pa, 80, 256);
+  int rc = gemm(mels_in, T[aci::PRE1_W], D[D_ZERO], pa, 80, 256, WP_PRE1);
   if (rc) return rc;
   prenet_act_kernel<<<act_grid, 256, 0, st>>>(pa, keep, seed, mode, 0, B, N, pb, 256);
   ctx->launches++;
-  rc = gemm(pb, T[aci::PRE2_W], D[D_ZERO], pa, 256, 256);
+  rc = gemm(pb, T[aci::PRE2_W], D[D_ZERO], pa, 256, 256, WP_PRE2);
   if (rc) return rc;
   prenet_act_kernel<<<act_grid, 256, 0, st>>>(pa, keep, seed, mode, 1, B, N, xin + vc::ENC_OUT, XW);
   ctx->launches++;
@@ -1241,8 +1261,9 @@ int vtts_acoustic_teacher_run(vtts_ctx* ctx, const int32_t* tokens, const int32_
   Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0; Lc.len_mul = 1;
   Lc.p[0] = ConvProb{xin, nullptr, nullptr, T[aci::DEC_L0_W], T[aci::DEC_L0_B], nullptr, nullptr, nullptr, nullptr, zc0, 1, 1, 0, 1, 0};
   Lc.p[1] = ConvProb{xin, nullptr, nullptr, T[aci::DEC_L1_W], T[aci::DEC_L1_B], nullptr, nullptr, nullptr, nullptr, zc1, 1, 1, 0, 1, 0};
-  rc = vtts_launch_conv(ctx, Lc, st);
+  rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_TF_L0], st);      // tiles of problem 0 then problem 1: WP_TF_L0 .. WP_TF_L1+7
   if (rc) return rc;
+  ctx->sub_mark(18, st);
   // ---- zoneout scan, <= 32 rows per launch ----
   for (int b0 = 0; b0 < B; b0 += DEC_XR) {
     const int nb = B - b0 < DEC_XR ? B - b0 : DEC_XR;
@@ -1257,15 +1278,18 @@ int vtts_acoustic_teacher_run(vtts_ctx* ctx, const int32_t* tokens, const int32_
     VTTS_CUDA(cudaLaunchCooperativeKernel((void*)decoder_tf_scan_kernel, dim3(SCAN_CTAS), dim3(SCAN_THREADS), args, tf_scan_smem(), st));
     ctx->launches++;
   }
+  ctx->sub_mark(19, st);
   // ---- projection over all frames, then the postnet ----
   memset(&Lc, 0, sizeof(Lc));
   Lc.nprob = 1; Lc.Cin = 1024; Lc.Cout = 80; Lc.B = B; Lc.T_rows = N; Lc.rows_out = N;
   Lc.len = n_frames; Lc.len_mul = 1; Lc.pre_mode = 0; Lc.pre_slope = 1.f; Lc.post_act = 0;      // rows past n_frames[b] stay 0
   Lc.p[0] = ConvProb{hout, nullptr, nullptr, T[aci::PROJ_W], T[aci::PROJ_B], nullptr, nullptr, nullptr, nullptr, melpre, 1, 1, 0, 1, 0};
-  rc = vtts_launch_conv(ctx, Lc, st);
+  rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_PROJ], st);
   if (rc) return rc;
   if (mel1) VTTS_CUDA(cudaMemcpyAsync(mel1, melpre, BN * 80 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel2, st);
+  rc = run_postnet(ctx, melpre, n_frames, B, N, q0, q1, mel2, st);
+  ctx->sub_mark(20, st);
+  return rc;
 }
 
 // =====================================================================================================

@@ -206,6 +206,21 @@ struct vtts_ctx {
   cudaStream_t ev_stream[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid[NSTAGE] = {false, false, false, false};
 
+  // optional sub-stage timers (vtts_debug_substages): CUDA events recorded between the kernels of a forward call.
+  // ids: acoustic 0 start | 1 encoder | 2 upsample | 3 hoisted cond GEMMs | 4 decoder scan | 5 projection | 6 postnet
+  //      hifigan  8 start | 9 conv_pre | 10..13 stage 0..3 (ConvTranspose + 3 ResBlocks) | 14 conv_post
+  //      teacher  16 start | 17 encoder+upsample | 18 prenet+hoisted GEMMs | 19 zoneout scan | 20 projection+postnet
+  static constexpr int NSUB = 24;
+  bool sub_on = false;
+  cudaEvent_t sub_ev[NSUB] = {};
+  bool sub_set[NSUB] = {};
+  void sub_mark(int id, cudaStream_t st) {
+    if (!sub_on) return;
+    if (!sub_ev[id]) cudaEventCreate(&sub_ev[id]);
+    cudaEventRecord(sub_ev[id], st);
+    sub_set[id] = true;
+  }
+
   int fail(int code, const char* fmt, ...);
   int ensure_ws(size_t bytes);
   int ensure_staging(size_t host_bytes, size_t dev_bytes);

@@ -13,6 +13,12 @@ import numpy as np
 from . import _lib, config, weights
 
 DROPOUT_OFF, DROPOUT_MASK, DROPOUT_SEED = 0, 1, 2
+
+
+def _chunk_seed(seed: int, chunk: int) -> int:
+    """Key of the on-device dropout stream for the chunk-th slice of an over-long batch (a distinct 64-bit key per
+    chunk: `seed + offset` would alias the next seed's first chunk)."""
+    return (int(seed) ^ (chunk * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
 PRECISION_FP32, PRECISION_BF16X3 = 0, 1
 MAX_ACOUSTIC_ROWS = 128   # rows per vtts_acoustic_forward call (csrc/nat.cu MAX_ROWS)
 
@@ -113,6 +119,18 @@ class Engine:
         flags = (1 if enable else 0) | (0 if variant is None else (0x100 | (int(variant) << 4)))
         self._ck(self.lib.vtts_debug_tc_stats(self.h, flags, _ptr(out)))
         return out
+
+    SUBSTAGES = {1: "acoustic.encoder", 2: "acoustic.upsample", 3: "acoustic.cond_gemm", 4: "acoustic.decoder_scan",
+                 5: "acoustic.projection", 6: "acoustic.postnet", 9: "hifigan.conv_pre", 10: "hifigan.stage0", 11: "hifigan.stage1",
+                 12: "hifigan.stage2", 13: "hifigan.stage3", 14: "hifigan.conv_post", 17: "teacher.encoder_upsample",
+                 18: "teacher.prenet_hoisted_gemm", 19: "teacher.zoneout_scan", 20: "teacher.projection_postnet"}
+
+    def substages(self, enable=True) -> dict:
+        """Per-kernel-group device times (ms) of the forward calls since the previous call (vtts_debug_substages);
+        `enable` switches the event recording on/off for the following calls."""
+        out = np.zeros(24, np.float32)
+        self._ck(self.lib.vtts_debug_substages(self.h, 1 if enable else 0, _ptr(out)))
+        return {name: float(out[i]) for i, name in self.SUBSTAGES.items() if out[i] > 0}
 
     # ---- weights ----
     def load_hifigan(self, params, key=None):
@@ -227,7 +245,8 @@ class Engine:
             out = np.empty((b1 - b0, N, config.MEL_DIM), np.float32)
             self._ck(self.lib.vtts_predict_mel_host(
                 self.h, _ptr(tokens[sl]), _ptr(None if lens is None else lens[sl]), _ptr(dur[sl]), _ptr(nf[sl]),
-                _ptr(None if masks is None else np.ascontiguousarray(masks[sl])), mode, seed + b0, b1 - b0, L, N, _ptr(out)))
+                _ptr(None if masks is None else np.ascontiguousarray(masks[sl])), mode, _chunk_seed(seed, b0 // MAX_ACOUSTIC_ROWS),
+                b1 - b0, L, N, _ptr(out)))
             mel[sl] = out
         return mel
 
@@ -268,28 +287,23 @@ class Engine:
     def synthesize(self, tokens, dur_frames, lengths=None, n_frames=None, masks=None, seed=None, return_mel=False, out=None):
         """predict_mel -> mel2wave with the mel staying on the device.  Returns wav [B,256N]
         (and mel [B,N,80] if return_mel).  `out`: optional preallocated float32 [B,256N] result array
-        (ideally from `pinned_empty`)."""
+        (ideally from `pinned_empty`); it is validated and written in every path (rows land directly in it).
+        In SEED mode row r of a call draws the device stream keyed by (seed, r, frame): an utterance's masks depend on
+        its row index, not on the padded frame count of the batch; MASK / OFF modes are position independent."""
         tokens, dur, lens, nf, N, masks, mode, seed = self._acoustic_args(tokens, dur_frames, lengths, n_frames, masks, seed)
         B, L = tokens.shape
-        if out is not None and B <= MAX_ACOUSTIC_ROWS and not return_mel:
-            if out.shape != (B, N * config.HOP) or out.dtype != np.float32 or not out.flags.c_contiguous:
-                raise ValueError(f"out must be C-contiguous float32 {(B, N * config.HOP)}")
-            self._ck(self.lib.vtts_synthesize_host(
-                self.h, _ptr(tokens), _ptr(lens), _ptr(dur), _ptr(nf), _ptr(masks), mode, seed, B, L, N, None, _ptr(out)))
-            return out
-        wav = np.empty((B, N * config.HOP), np.float32)
+        if out is not None and (out.shape != (B, N * config.HOP) or out.dtype != np.float32 or not out.flags.c_contiguous):
+            raise ValueError(f"out must be C-contiguous float32 {(B, N * config.HOP)}")
+        wav = out if out is not None else np.empty((B, N * config.HOP), np.float32)
         mel = np.empty((B, N, config.MEL_DIM), np.float32) if return_mel else None
         for b0 in range(0, B, MAX_ACOUSTIC_ROWS):
             b1 = min(B, b0 + MAX_ACOUSTIC_ROWS)
             sl = slice(b0, b1)
-            w = np.empty((b1 - b0, N * config.HOP), np.float32)
-            m = np.empty((b1 - b0, N, config.MEL_DIM), np.float32) if return_mel else None
+            # row slices of C-contiguous arrays are contiguous: the library writes straight into the result
             self._ck(self.lib.vtts_synthesize_host(
                 self.h, _ptr(tokens[sl]), _ptr(None if lens is None else lens[sl]), _ptr(dur[sl]), _ptr(nf[sl]),
-                _ptr(None if masks is None else np.ascontiguousarray(masks[sl])), mode, seed + b0, b1 - b0, L, N, _ptr(m), _ptr(w)))
-            wav[sl] = w
-            if return_mel:
-                mel[sl] = m
+                _ptr(None if masks is None else np.ascontiguousarray(masks[sl])), mode, _chunk_seed(seed, b0 // MAX_ACOUSTIC_ROWS),
+                b1 - b0, L, N, _ptr(None if mel is None else mel[sl]), _ptr(wav[sl])))
         return (wav, mel) if return_mel else wav
 
     def tts(self, tokens, lengths=None, silence_duration=-1.0, seed=None, max_frames=None):

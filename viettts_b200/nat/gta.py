@@ -10,18 +10,22 @@ from pathlib import Path
 
 import numpy as np
 
-from .. import config
-from .text2mel import load_acoustic
+from .. import config, jaxrng
+from .text2mel import checkpoint_rng, load_acoustic
 
 
 def forward_fn(wavs, phonemes, lengths, durations, wav_lengths=None, keep_masks=None, zone_masks=None, seed=None, engine=None):
     """gta.py:28-44.  wavs int16 [B,S]; phonemes int [B,L]; lengths int [B]; durations f32 [B,L] SECONDS.
-    Returns mel2_hat f32 [B,S/256,80].  The prenet dropout and zoneout masks come from `keep_masks`/`zone_masks`
-    (e.g. dumped from a JAX run) or from the on-device stream keyed by `seed` (default: the checkpoint's rng)."""
-    engine, ck_seed = load_acoustic(engine)
+    Returns mel2_hat f32 [B,S/256,80] over the FULL padded length: like the reference's `forward_fn_`, the model never
+    sees `wav_lengths` (the postnet runs over all S/256 frames; gta.py:70-76 only slices `mel[idx, :l]` when saving),
+    so `wav_lengths` is accepted for signature compatibility and used by `save_batch` alone.
+    Masks: `keep_masks`/`zone_masks` explicitly, else `seed` for the library's on-device stream, else (default) the
+    masks the reference itself draws from the checkpoint's rng (Haiku split chain, `viettts_b200.jaxrng`)."""
+    engine, _ = load_acoustic(engine)
     if keep_masks is None and seed is None:
-        seed = ck_seed
-    return engine.gta(wavs, phonemes, durations, lengths=lengths, wav_lengths=wav_lengths, keep_masks=keep_masks,
+        wavs_a = np.asarray(wavs)
+        keep_masks, zone_masks = jaxrng.teacher_forced_masks(checkpoint_rng(), wavs_a.shape[0], wavs_a.shape[1] // config.HOP)
+    return engine.gta(wavs, phonemes, durations, lengths=lengths, wav_lengths=None, keep_masks=keep_masks,
                       zone_masks=zone_masks, seed=seed)
 
 

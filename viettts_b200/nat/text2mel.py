@@ -7,18 +7,21 @@ step/params/aux/rng/optim_state) and returns mel f32 [1,N,80] with
 N = int(sum(durations*16000/256)).
 
 Dropout: the reference applies prenet dropout at inference with the
-checkpoint's `rng` through JAX's threefry stream (nat/model.py:95-100,132).
-That stream cannot be reproduced without JAX, so by default the masks are drawn
-on the device from a threefry2x32 counter stream keyed by the checkpoint's rng
-words; pass `masks=` (uint8 [1,N,2,256], e.g. dumped from the real JAX run) for
-bit-identical masks, or `dropout=False` for the deterministic mode."""
+checkpoint's `rng` through Haiku's split chain on JAX's threefry generator
+(nat/model.py:95-100,132).  That is a pure function of the two rng words, which
+`viettts_b200.jaxrng` restates on the host, so by default `predict_mel` feeds the
+device exactly the keep-masks the reference would draw (sample-wise parity with
+the JAX path, classic threefry layout).  `seed=` selects the library's own
+on-device counter stream instead (no host mask generation, used by the batched
+throughput paths), `masks=` (uint8 [1,N,2,256]) supplies masks explicitly, and
+`dropout=False` is the deterministic mode."""
 from __future__ import annotations
 
 import os
 
 import numpy as np
 
-from .. import config
+from .. import config, jaxrng
 from ..engine import get_engine
 from ..weights import load_pickle
 
@@ -32,18 +35,29 @@ def _file_key(path):
 
 
 _rng_words = {}
+_rng_keys = {}
 
 
 def load_acoustic(engine=None, ckpt_file=None):
+    """Loads the checkpoint into the engine once per file version; returns (engine, rng words as one uint64)."""
     engine = engine or get_engine()
     ckpt_file = ckpt_file or CKPT_FILE
     key = _file_key(ckpt_file)
-    if engine._acoustic_key != key:
+    if engine._acoustic_key != key or key not in _rng_words:
         dic = load_pickle(ckpt_file)
         engine.load_acoustic(dic, key=key)
         rng = np.asarray(dic.get("rng", [0, 42])).astype(np.uint64).ravel()
         _rng_words[key] = int((int(rng[0]) << 32) | int(rng[-1]))
+        _rng_keys[key] = np.array([rng[0], rng[-1]], np.uint32)
     return engine, _rng_words.get(key, 42)
+
+
+def checkpoint_rng(ckpt_file=None) -> np.ndarray:
+    """The checkpoint's `rng` (text2mel.py:69), uint32[2]; the acoustic checkpoint must have been loaded."""
+    key = _file_key(ckpt_file or CKPT_FILE)
+    if key not in _rng_keys:
+        load_acoustic(ckpt_file=ckpt_file)
+    return _rng_keys[key]
 
 
 def seconds_to_frames(durations):
@@ -52,12 +66,17 @@ def seconds_to_frames(durations):
     return d, int(np.sum(d, dtype=np.float32))
 
 
-def predict_mel(tokens, durations, masks=None, dropout=True):
-    engine, seed = load_acoustic()
+def predict_mel(tokens, durations, masks=None, dropout=True, seed=None):
+    engine, _ = load_acoustic()
     d, n_frames = seconds_to_frames(durations)
     tokens = np.array(tokens, dtype=np.int32)[None, :]
     d = d.reshape(1, -1)
-    return engine.predict_mel(tokens, d, n_frames=[n_frames], masks=masks, seed=(seed if (dropout and masks is None) else None))
+    if not dropout:
+        masks, seed = None, None
+    elif masks is None and seed is None:
+        # the reference's own stream: hk.next_rng_key() chain from the checkpoint rng, two [1,256] draws per frame
+        masks = jaxrng.inference_keep_masks(checkpoint_rng(), 1, n_frames)
+    return engine.predict_mel(tokens, d, n_frames=[n_frames], masks=masks, seed=seed if masks is None else None)
 
 
 # ---------------------------------------------------------------------------
@@ -120,12 +139,12 @@ def adjust_durations(tokens, durations, silence_duration=-1.0):
     return d.astype(np.float32)
 
 
-def text2mel(text, lexicon_fn=None, silence_duration=-1.0, masks=None, dropout=True):
+def text2mel(text, lexicon_fn=None, silence_duration=-1.0, masks=None, dropout=True, seed=None):
     """text2mel.py:85-103: text -> tokens -> durations -> mel f32 [1,N',80]; the frames of the trailing
     silence token are cut (`:99-102`)."""
     tokens = text2tokens(text, lexicon_fn if lexicon_fn is not None else config.LEXICON_FILE)
     durations = adjust_durations(tokens, predict_duration(tokens), silence_duration)
-    mels = predict_mel(tokens, durations, masks=masks, dropout=dropout)
+    mels = predict_mel(tokens, durations, masks=masks, dropout=dropout, seed=seed)
     if tokens[-1] == config.SIL_INDEX:
         end_silence = float(durations[0, -1])
         silence_frame = int(end_silence * config.SAMPLE_RATE / (config.N_FFT // 4))

@@ -71,7 +71,9 @@ def synthesize_lines(lines, lexicon_file, silence_duration=-1.0, seed=None, max_
     from .nat import text2mel as t2m
     from .hifigan.mel2wave import load_generator
     engine = t2m.load_duration(engine)
-    t2m.load_acoustic(engine)
+    _, ck_seed = t2m.load_acoustic(engine)
+    if seed is None:
+        seed = ck_seed          # default stream key: the checkpoint's rng words, same as the single --text path
     load_generator(engine)
     toks = [t2m.text2tokens(nat_normalize_text(line), lexicon_file) for line in lines]
     order = sorted(range(len(toks)), key=lambda i: len(toks[i]))
@@ -98,13 +100,15 @@ def main(argv=None) -> int:
     parser.add_argument("--sample-rate", default=16000, type=int)
     parser.add_argument("--silence-duration", default=-1, type=float)
     parser.add_argument("--lexicon-file", default=None)
-    parser.add_argument("--seed", default=None, type=int, help="prenet dropout stream (default: the checkpoint's rng words)")
+    parser.add_argument("--seed", default=None, type=int,
+                        help="prenet dropout: key of the on-device counter stream; default = the checkpoint's rng "
+                             "(--text: the reference's own JAX/Haiku mask stream; --text-file: the device stream keyed by those words)")
     args = parser.parse_args(argv)
     lexicon = args.lexicon_file if args.lexicon_file is not None else config.LEXICON_FILE
 
     if args.text_file is not None:
         lines = [ln for ln in args.text_file.read_text().splitlines() if ln.strip()]
-        waves = synthesize_lines(lines, lexicon, args.silence_duration, seed=args.seed if args.seed is not None else 42)
+        waves = synthesize_lines(lines, lexicon, args.silence_duration, seed=args.seed)
         for i, w in enumerate(waves):
             fn = args.output.with_name(f"{args.output.stem}_{i:04d}{args.output.suffix or '.wav'}")
             print("writing output to file", fn)
@@ -117,7 +121,7 @@ def main(argv=None) -> int:
     from .nat.text2mel import text2mel
     text = nat_normalize_text(args.text)
     print("Normalized text input:", text)
-    mel = text2mel(text, lexicon, args.silence_duration)
+    mel = text2mel(text, lexicon, args.silence_duration, seed=args.seed)
     wave = mel2wave(mel)
     print("writing output to file", args.output)
     write_wav(args.output, wave, args.sample_rate)

@@ -94,8 +94,13 @@ def load_pickle(path):
         data = f.read()
     try:
         return _plain(_Unpickler(io.BytesIO(data)).load())
-    except Exception:
-        return pickle.loads(data)
+    except (ModuleNotFoundError, AttributeError, ImportError) as first:
+        # a class the jax-free unpickler does not know: only the real modules can resolve it.  Any other failure
+        # (e.g. the explicit UnpicklingError of _FlatMapping.__setstate__) propagates unchanged.
+        try:
+            return pickle.loads(data)
+        except Exception as second:
+            raise second from first
 
 
 # ---------------------------------------------------------------------------
