@@ -193,8 +193,7 @@ def run_reference(args):
     rows = args.ref_rows
     tokens, durs, nfs = make_batch(rows, args.phonemes, args.seconds, 0)
     masks = synthetic.dropout_masks(3, rows, int(nfs[0]))
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_port_step(hp, ck, tokens, durs, nfs, masks)
+    cpu_port_step(hp, ck, tokens[:1], durs[:1], nfs[:1], masks[:1])      # one warm-up pass (the CPU port has no compile / cache state to warm)
     t0 = time.perf_counter()
     samples = 0
     for _ in range(args.steps):
@@ -206,14 +205,155 @@ def run_reference(args):
     out = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                rtf=(dt / (samples / C.SAMPLE_RATE)),
-               config=dict(workload=f"NAT acoustic + HiFiGAN, {args.phonemes}-phoneme / {args.seconds:g} s utterances, batch {args.batch} per GPU",
-                           sample=f"{rows} utterance(s) per step (bounded sample of the batch-{args.batch} workload)"),
+               config=workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
                cpu_baseline=dict(value=val, unit=UNIT, cores=max(th.values()), kind="port", sample=desc),
                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+# algorithmic FLOPs per mel frame of each generator sub-stage (2 x MACs; sums to 614 105 088)
+_HG_MAC = dict(conv_pre=7 * 80 * 512, conv_post=256 * 7 * 32,
+               stage0=8 * 256 * 256 * 126 + 8 * 2 * 512 * 256, stage1=64 * 128 * 128 * 126 + 64 * 2 * 256 * 128,
+               stage2=128 * 64 * 64 * 126 + 128 * 2 * 128 * 64, stage3=256 * 32 * 32 * 126 + 256 * 2 * 64 * 32)
+assert 2 * sum(_HG_MAC.values()) == C.HIFIGAN_FLOP_PER_FRAME, sum(_HG_MAC.values())
+
+
+def workload_config(args, world):
+    """The `config` object both arms print (identical content, so the driver's same_config check can hold)."""
+    n = int(args.seconds * C.SAMPLE_RATE / C.HOP)
+    return dict(workload=f"NAT acoustic + HiFiGAN, {args.phonemes}-phoneme / {args.seconds:g} s utterances, batch {args.batch} per GPU (BASELINE configs[2])",
+                batch_per_gpu=args.batch, phonemes=args.phonemes, mel_frames=n, samples_per_utterance=n * C.HOP,
+                parallelism=f"utterance-sharded x{world}",
+                l2="activations per step (>4 GB) exceed the 126 MB L2; no flush needed", dropout="on-device threefry keep-masks")
+
+
+class Job:
+    """One batch resident on the device + the calls that time it."""
+
+    def __init__(self, eng, dev, tokens, durs, nfs, seed, lengths=None):
+        import torch
+        self.eng, self.dev = eng, dev
+        self.tokens, self.durs, self.nfs, self.seed, self.lengths = tokens, durs, nfs, seed, lengths
+        self.B, self.L = tokens.shape
+        self.N = int(nfs.max())
+        self.tok_t = torch.from_numpy(tokens).to(dev)
+        self.dur_t = torch.from_numpy(durs).to(dev)
+        self.nf_t = torch.from_numpy(nfs).to(dev)
+        self.len_t = None if lengths is None else torch.from_numpy(lengths).to(dev)
+        self.mel_t = torch.empty((self.B, self.N, C.MEL_DIM), dtype=torch.float32, device=dev)
+        self.wav_t = torch.empty((self.B, self.N * C.HOP), dtype=torch.float32, device=dev)
+        self.samples = int(nfs.sum()) * C.HOP
+        self.frames = int(nfs.sum())
+
+    def step(self, marks=None):
+        e = self.eng
+        if marks is not None:
+            marks[0].record()
+        e.acoustic_forward(self.tok_t, self.dur_t, self.N, lengths_t=self.len_t, n_frames_t=self.nf_t, seed=self.seed, out=self.mel_t)
+        if marks is not None:
+            marks[1].record()
+        e.hifigan_forward(self.mel_t, self.nf_t, out=self.wav_t)
+        if marks is not None:
+            marks[2].record()
+
+
+def time_jobs(jobs, steps, warmup, barrier):
+    """CUDA-event time of `steps` passes over the jobs of this rank (device-resident inputs)."""
+    import torch
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    for _ in range(warmup):
+        for j in jobs:
+            j.step()
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
+    marks = [[[ev(), ev(), ev()] for _ in jobs] for _ in range(steps)]
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(steps):
+        for ji, j in enumerate(jobs):
+            j.step(marks[k][ji])
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    ac = float(np.sum([[m[0].elapsed_time(m[1]) for m in row] for row in marks])) / steps
+    hg = float(np.sum([[m[1].elapsed_time(m[2]) for m in row] for row in marks])) / steps
+    return ms, ac, hg
+
+
+def time_e2e(eng, job, steps, out):
+    """Wall time of `steps` host-buffer calls (numpy in -> H2D -> kernels -> D2H -> numpy out)."""
+    for _ in range(2):
+        eng.synthesize(job.tokens, job.durs, lengths=job.lengths, n_frames=job.nfs, seed=job.seed, out=out)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w = eng.synthesize(job.tokens, job.durs, lengths=job.lengths, n_frames=job.nfs, seed=job.seed, out=out)
+    return (time.perf_counter() - t0) / steps, w
+
+
+def stage_rooflines(eng, job, pk, precision):
+    """One entry per kernel group of the step: device ms (CUDA events between the kernels, vtts_debug_substages), the
+    algorithmic work of SURVEY.md §8(d) and the bound it is measured against."""
+    import torch
+    eng.substages(True)
+    job.step()
+    torch.cuda.synchronize()
+    ms = eng.substages(False)
+    rows, frames = job.B, job.frames
+    hbm = pk["hbm_gbs"]
+    tc_ceiling = pk["bf16_tflops_sustained"] / 3.0 if precision != "fp32" else 74.4
+    out = {}
+
+    def tensor(name, key, flop, note=None):
+        if key not in ms:
+            return
+        t = flop / (ms[key] / 1e3) / 1e12
+        out[name] = dict(ms=ms[key], bound="tensor (bf16x3: 1/3 of the measured sustained bf16 peak)" if precision != "fp32" else "fp32 FMA pipe",
+                         achieved_tflops=t, frac_of_ceiling=t / tc_ceiling, algorithmic_flop=flop)
+        if note:
+            out[name]["note"] = note
+
+    for i in range(4):
+        tensor(f"hifigan_stage{i}", f"hifigan.stage{i}", 2.0 * _HG_MAC[f"stage{i}"] * frames)
+    tensor("hifigan_conv_pre", "hifigan.conv_pre", 2.0 * _HG_MAC["conv_pre"] * frames)
+    if "hifigan.conv_post" in ms:
+        byts = frames * 256 * (3 * 32 * 4 + 4)          # reads the three ResBlock outputs, writes one sample
+        g = byts / (ms["hifigan.conv_post"] / 1e3) / 1e9
+        out["hifigan_conv_post"] = dict(ms=ms["hifigan.conv_post"], bound="hbm", achieved_gbs=g, frac_hbm=g / hbm, algorithmic_bytes=byts)
+    if "acoustic.decoder_scan" in ms:
+        t = ms["acoustic.decoder_scan"]
+        launches = (rows + 127) // 128
+        out["nat_decoder_scan"] = dict(ms=t, bound="latency (sequential over frames; weights resident on chip)", us_per_frame=1e3 * t / (job.N * launches),
+                                       rows=rows, frames=job.N, achieved_tflops_fp32=12_918_784.0 * frames / (t / 1e3) / 1e12,
+                                       note="12 918 784 FLOP per frame per row (SURVEY 8d); cond projections hoisted into acoustic.cond_gemm")
+    tensor("nat_cond_gemm", "acoustic.cond_gemm", 2.0 * 512 * 4096 * frames, "hoisted cond . W[0:512] of both decoder LSTMs")
+    tensor("nat_postnet", "acoustic.postnet", 8_683_520.0 * frames)
+    tensor("nat_projection", "acoustic.projection", 2.0 * 1024 * 80 * frames)
+    if "acoustic.upsample" in ms:
+        byts = rows * job.L * 2048 + frames * 2048
+        g = byts / (ms["acoustic.upsample"] / 1e3) / 1e9
+        out["nat_upsample"] = dict(ms=ms["acoustic.upsample"], bound="hbm/L2", achieved_gbs=g, frac_hbm=g / hbm, algorithmic_bytes=byts)
+    if "acoustic.encoder" in ms:
+        out["nat_token_encoder"] = dict(ms=ms["acoustic.encoder"], bound="latency (BiLSTM scan over tokens)", us_per_token=1e3 * ms["acoustic.encoder"] / job.L)
+    return out
+
+
+def c5_workload(n=256, seed0=5000):
+    """BASELINE configs[4]: n utterances, L ~ U{50..300} phonemes at ~0.05 s per phoneme."""
+    rng = np.random.default_rng(77)
+    utts = []
+    for i in range(n):
+        L = int(rng.integers(50, 301))
+        tk, d = synthetic.utterance(seed0 + i, L, None)
+        d = (np.asarray(d, np.float32) * np.float32(C.SAMPLE_RATE)) / np.float32(C.HOP)
+        utts.append((np.asarray(tk, np.int32), d[0], int(np.sum(d, dtype=np.float32))))
+    return utts
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -234,89 +374,145 @@ def run_ours(args):
 
     eng = Engine(local)
     eng.set_precision(args.precision)
+    if args.pairs != "auto":
+        eng.set_fused_pairs(args.pairs != "off", ts=args.pairs != "smem")
     hp = synthetic.hifigan_params(1234) if rank == 0 else None
     ck = synthetic.acoustic_ckpt(1234) if rank == 0 else None
     t_w = time.perf_counter()
     wbytes = parallel.load_weights_distributed(eng, hp, ck, dev)
     t_w = time.perf_counter() - t_w
 
-    B = args.batch
-    tokens, durs, nfs = make_batch(B, args.phonemes, args.seconds, 1000 * rank)
-    N = int(nfs.max())
-    L = tokens.shape[1]
-    seed = 0xC0FFEE + rank
-    tok_t = torch.from_numpy(tokens).to(dev)
-    dur_t = torch.from_numpy(durs).to(dev)
-    nf_t = torch.from_numpy(nfs).to(dev)
-    mel_t = torch.empty((B, N, C.MEL_DIM), dtype=torch.float32, device=dev)
-    wav_t = torch.empty((B, N * C.HOP), dtype=torch.float32, device=dev)
-    samples_step = int(nfs.sum()) * C.HOP
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-
-    def step(marks=None):
-        if marks is not None:
-            marks[0].record()
-        eng.acoustic_forward(tok_t, dur_t, N, n_frames_t=nf_t, seed=seed, out=mel_t)
-        if marks is not None:
-            marks[1].record()
-        eng.hifigan_forward(mel_t, nf_t, out=wav_t)
-        if marks is not None:
-            marks[2].record()
-
     def barrier():
         if world > 1:
             dist.barrier()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allgather(x):
+        if world == 1:
+            return [float(x)]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        outl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outl, t)
+        return [float(o.item()) for o in outl]
+
+    W = max(args.warmup, 3)
+    side_steps = max(3, min(args.steps, 5))
+    pk = peaks()
+
+    # ================= headline: BASELINE configs[2], weak scaling, 32 utterances per GPU =================
+    B = args.batch
+    tokens, durs, nfs = make_batch(B, args.phonemes, args.seconds, 1000 * rank)
+    job = Job(eng, dev, tokens, durs, nfs, 0xC0FFEE + rank)
+    N, L = job.N, job.L
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    torch.cuda.synchronize()
     l0 = eng.launch_count()
-    marks = [[ev(), ev(), ev()] for _ in range(args.steps)]
-    e0, e1 = ev(), ev()
-    e0.record()
-    for k in range(args.steps):
-        step(marks[k])
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    launches = eng.launch_count() - l0
+    ms_step, ac_ms, hg_ms = time_jobs([job], args.steps, W, barrier)
+    launches = (eng.launch_count() - l0) * args.steps // (args.steps + W)
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = e0.elapsed_time(e1)
-    ac_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
-    hg_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * samples_step / (ms_step / 1e3)
+    ms_step = allmax(ms_step)
+    value = world * job.samples / (ms_step / 1e3)
 
-    # ---- e2e through the host-buffer C ABI ----
-    wav_pinned = Engine.pinned_empty((B, N * C.HOP))          # page-locked result buffer, reused every step
-    for _ in range(2):
-        eng.synthesize(tokens, durs, n_frames=nfs, seed=seed, out=wav_pinned)
+    # ---- e2e through the host-buffer C ABI: page-locked result buffer (headline) and a pageable numpy result ----
+    wav_pinned = Engine.pinned_empty((B, N * C.HOP))
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        wav_h = eng.synthesize(tokens, durs, n_frames=nfs, seed=seed, out=wav_pinned)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_val = world * samples_step * args.steps / dt
+    dt, wav_h = time_e2e(eng, job, args.steps, wav_pinned)
+    dt = allmax(dt)
+    e2e_val = world * job.samples / dt
+    dt_pg, _ = time_e2e(eng, job, side_steps, np.empty((B, N * C.HOP), np.float32))
+    dt_pg = allmax(dt_pg)
     h2d = tokens.nbytes + durs.nbytes + nfs.nbytes
     d2h = wav_h.nbytes
 
-    # ---- STFT/log-mel kernel (MelFilter, nat/dsp.py:104-128): HBM-bound streaming kernel, measured separately ----
+    def line_for(jobs, steps, scaling_world=world, e2e_job=None):
+        ms, ac, hg = time_jobs(jobs, steps, 3, barrier)
+        per_rank = allgather(ms)
+        ms_max = max(per_rank)
+        samples = sum(j.samples for j in jobs)
+        tot = samples
+        if world > 1:
+            t = torch.tensor([samples], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            tot = float(t.item())
+        d = dict(value=tot / (ms_max / 1e3), unit=UNIT, ms_per_step=ms_max, stages_ms=dict(acoustic=ac, hifigan=hg),
+                 rtf=(ms_max / 1e3) / (tot / C.SAMPLE_RATE), per_rank_busy_ms=per_rank,
+                 imbalance_max_over_mean=ms_max / (sum(per_rank) / len(per_rank)))
+        if e2e_job is not None:
+            o = Engine.pinned_empty((e2e_job.B, e2e_job.N * C.HOP))
+            dte, _ = time_e2e(eng, e2e_job, steps, o)
+            d["e2e_value"] = e2e_job.samples / dte
+        return d
+
+    # ================= batch sweep and strict-fp32 line (N = 1 only; north_star: batch 1/8/32/128) =================
+    sweep, strict = None, None
+    if world == 1 and not args.no_sweep:
+        sweep = {str(B): dict(value=value, ms_per_step=ms_step, stages_ms=dict(acoustic=ac_ms, hifigan=hg_ms), e2e_value=e2e_val,
+                              rtf=(ms_step / 1e3) / (job.samples / C.SAMPLE_RATE))}
+        for b2 in (1, 8, 128):
+            if b2 == B:
+                continue
+            t2, d2, n2 = make_batch(b2, args.phonemes, args.seconds, 7000)
+            j2 = Job(eng, dev, t2, d2, n2, 0xC0FFEE)
+            r = line_for([j2], side_steps, e2e_job=j2)
+            sweep[str(b2)] = {k: r[k] for k in ("value", "ms_per_step", "stages_ms", "e2e_value", "rtf")}
+            del j2
+        if args.precision != "fp32":
+            eng.set_precision("fp32")
+            r = line_for([job], 3, e2e_job=job)
+            strict = dict(dtype="f32 (IEEE fp32 FMA on the CUDA cores, conv1d.cu)", batch=B,
+                          **{k: r[k] for k in ("value", "ms_per_step", "stages_ms", "e2e_value", "rtf")})
+            eng.set_precision(args.precision)
+
+    # ================= BASELINE configs[3]: 128 utterances sharded over the ranks (strong scaling) =================
+    configs = {}
+    if not args.no_configs:
+        tk4, du4, nf4 = make_batch(128, args.phonemes, args.seconds, 31000)
+        shard = sorted(parallel.lpt_shard(nf4, world)[rank])
+        j4 = Job(eng, dev, tk4[shard], du4[shard], nf4[shard], 0xC4)
+        r = line_for([j4], side_steps)
+        configs["c4"] = dict(workload="128 x 100-phoneme / 5 s utterances, LPT-sharded by n_frames over the ranks (BASELINE configs[3])",
+                             scaling="strong", rows_per_gpu=len(shard), **r)
+        del j4
+        # ================= BASELINE configs[4]: n=256 mixed 50-300 phonemes, bucketed <= 8 % padding =================
+        utts = c5_workload()
+        nfs5 = [u[2] for u in utts]
+        buckets = parallel.bucket_by_length(nfs5, 0.08, max_rows=args.c5_rows)
+        # cost model of one bucket: the scan is paid per frame of its longest row, the generator per padded row-frame
+        cost = [int(max(nfs5[i] for i in bk) * (22.0 + 1.9 * len(bk))) for bk in buckets]
+        mine = parallel.lpt_shard(cost, world)[rank]
+        jobs5 = []
+        for bi in mine:
+            bk = buckets[bi]
+            Lm = max(len(utts[i][0]) for i in bk)
+            tk = np.zeros((len(bk), Lm), np.int32)
+            du = np.zeros((len(bk), Lm), np.float32)
+            ln = np.zeros(len(bk), np.int32)
+            for r_, i in enumerate(bk):
+                tk[r_, : len(utts[i][0])] = utts[i][0]
+                du[r_, : len(utts[i][0])] = utts[i][1]
+                ln[r_] = len(utts[i][0])
+            jobs5.append(Job(eng, dev, tk, du, np.asarray([nfs5[i] for i in bk], np.int32), 0xC5, lengths=ln))
+        r = line_for(jobs5, side_steps)
+        padded = sum(len(bk) * max(nfs5[i] for i in bk) for bk in buckets)
+        configs["c5"] = dict(workload="256 utterances, 50-300 phonemes (156-937 frames), bucketed by frame count and LPT-assigned to the ranks "
+                                      "(BASELINE configs[4])", scaling="strong", n_utterances=len(utts), n_buckets=len(buckets),
+                             max_rows_per_bucket=args.c5_rows, padding_frac=1.0 - sum(nfs5) / padded, buckets_on_this_rank=len(mine), **r)
+        del jobs5
+
+    # ================= per-stage rooflines (rank 0) =================
+    stages = stage_rooflines(eng, job, pk, args.precision) if rank == 0 else None
+
+    # ---- STFT/log-mel kernel (MelFilter, nat/dsp.py:104-128), measured separately ----
     mel_info = None
     if rank == 0:
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
         S = 79872
         MB = 512                                     # 512 x 5 s = 164 MB of samples: larger than L2
         wav_m = torch.rand((MB, S), dtype=torch.float32, device=dev) - 0.5
@@ -331,19 +527,22 @@ def run_ours(args):
         torch.cuda.synchronize()
         mms = m0.elapsed_time(m1) / 5
         mbytes = MB * S * 5.25                      # 4 B in + 1.25 B out per sample
-        pkm = peaks()
         mflop = MB * (S // C.HOP) * 29704.0         # sparse-filterbank FLOP count per frame
         mel_info = dict(samples_per_s=MB * S / (mms / 1e3), ms=mms, achieved_gbs=mbytes / (mms / 1e3) / 1e9,
-                        peak_gbs=pkm["hbm_gbs"], frac_hbm=mbytes / (mms / 1e3) / 1e9 / pkm["hbm_gbs"],
+                        peak_gbs=pk["hbm_gbs"], frac_hbm=mbytes / (mms / 1e3) / 1e9 / pk["hbm_gbs"],
                         achieved_tflops_fp32=mflop / (mms / 1e3) / 1e12, batch=MB, samples_per_row=S,
                         fp32_peak_tflops=74.4, frac_fp32=mflop / (mms / 1e3) / 1e12 / 74.4,
                         note="one warp per frame pair, FFT-1024 = 32 x 32 four-step with register-resident 32-point transforms; arithmetic intensity "
                              "22 FLOP/B sits above the FP32 ridge (11 FLOP/B): the kernel is FP32-issue bound, not HBM bound")
+        if stages is not None:
+            stages["melspec"] = dict(ms=mms, bound="hbm target (SURVEY 8d), fp32-issue bound in practice", achieved_gbs=mel_info["achieved_gbs"],
+                                     frac_hbm=mel_info["frac_hbm"], frac_fp32=mel_info["frac_fp32"])
         del wav_m, mel_m
 
-    # ---- callers of the path: duration model + one-call token->wav, chunked vocoding latency ----
+    # ---- callers of the path: duration model + one-call token->wav, chunked vocoding latency, GTA ----
     callers = None
-    if rank == 0 and world == 1 and not args.no_callers:     # side measurements at N=1 only, like cpu_baseline
+    if rank == 0 and world == 1 and not args.no_callers:
+        seed = job.seed
         eng.load_duration(synthetic.duration_ckpt(1234))
         for _ in range(2):
             waves, _ = eng.tts(tokens, silence_duration=0.05, seed=seed)
@@ -364,22 +563,23 @@ def run_ours(args):
         t0 = time.perf_counter()
         n_stream = sum(p.size for p in eng.mel2wave_stream(mel1, chunk_frames=32))
         all_ms = (time.perf_counter() - t0) * 1e3
-        # GTA forward (gta.py:28-41): int16 audio -> MelFilter -> teacher-forced acoustic model with zoneout
         eng.load_mel_filterbank()
         S_g = N * C.HOP
         wav_i16 = (np.random.default_rng(1).standard_normal((B, S_g)) * 3000).astype(np.int16)
         dur_sec = durs * np.float32(C.HOP / C.SAMPLE_RATE)
         for _ in range(2):
             eng.gta(wav_i16, tokens, dur_sec, seed=seed)
+        eng.substages(True)
         t0 = time.perf_counter()
         for _ in range(reps):
             eng.gta(wav_i16, tokens, dur_sec, seed=seed)
         dt_gta = (time.perf_counter() - t0) / reps
         gta_dev_ms = eng.last_stage_ms(1)
+        gta_sub = {k: v for k, v in eng.substages(False).items() if k.startswith("teacher.")}
         callers = dict(
             gta=dict(api="vtts_gta_host (int16 audio -> log-mel -> shift -> teacher-forced acoustic model, zoneout + dropout on), host buffers",
                      batch=B, frames_per_s=B * N / dt_gta, ms_per_call=dt_gta * 1e3, teacher_forced_model_ms=gta_dev_ms,
-                     autoregressive_model_ms=ac_ms),
+                     teacher_forced_stages_ms=gta_sub, autoregressive_model_ms=ac_ms),
             text_to_wav=dict(api="vtts_tts_host (duration model -> duration fix-ups -> acoustic -> trailing-silence trim -> generator), host buffers",
                              batch=B, samples_per_s=tts_samples / dt_tts, ms_per_call=dt_tts * 1e3, samples_per_call=tts_samples,
                              duration_model_ms=dur_ms),
@@ -388,35 +588,35 @@ def run_ours(args):
                                    whole_utterance_ms=all_ms, samples=n_stream))
 
     if rank == 0:
-        pk = peaks()
-        frames = int(nfs.sum())
+        frames = job.frames
         flops = frames * C.HIFIGAN_FLOP_PER_FRAME
         ach = flops / (hg_ms / 1e3) / 1e12
-        traffic = None
-        tp = REPO / "profiles" / "r1_traffic.json"
-        if tp.exists():
+        traffic, traffic_src = None, None
+        for tp in sorted((REPO / "profiles").glob("r*_traffic.json"), reverse=True):
             tj = json.loads(tp.read_text())
             w = tj.get("workload", {})
-            if w.get("batch") == B and w.get("mel_frames") == N and w.get("precision") == args.precision:
+            if w.get("batch") == B and w.get("mel_frames") == N and w.get("precision") == args.precision and w.get("pairs", "auto") == args.pairs:
                 traffic = tj["generator_dram_bytes_per_step"]
+                traffic_src = f"sum of dram__bytes_read+write over the generator launches of one step, ncu launch list of this command ({tp.name}); not re-measured in this run"
+                break
         ceiling = pk["bf16_tflops_sustained"] / 3.0 if args.precision != "fp32" else 74.4
         out = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=W, ms_per_step=ms_step,
             higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="f32" if args.precision == "fp32" else "f32 (bf16x3 split products on tcgen05, fp32 accumulate/storage)", data="synthetic",
-            rtf=(ms_step / 1e3) / (world * samples_step / C.SAMPLE_RATE),
-            config=dict(workload=f"NAT acoustic + HiFiGAN, {args.phonemes}-phoneme / {args.seconds:g} s utterances, batch {B} per GPU (BASELINE configs[2])",
-                        batch_per_gpu=B, phonemes=L, mel_frames=N, samples_per_utterance=N * C.HOP, parallelism=f"utterance-sharded x{world}",
-                        l2="activations per step (>4 GB) exceed the 126 MB L2; no flush needed", dropout="on-device threefry keep-masks"),
+            rtf=(ms_step / 1e3) / (world * job.samples / C.SAMPLE_RATE),
+            config=workload_config(args, world),
             stages_ms=dict(acoustic=ac_ms, hifigan=hg_ms),
-            e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt / args.steps,
-                     api="vtts_synthesize_host via viettts_b200.Engine.synthesize (numpy in; numpy out in a page-locked buffer the D2H copy lands in)"),
+            e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt,
+                     api="vtts_synthesize_host via viettts_b200.Engine.synthesize (numpy in; numpy out in a page-locked buffer the D2H copy lands in)",
+                     pageable_result=dict(value=world * job.samples / dt_pg, ms_per_step=1e3 * dt_pg,
+                                          note="same call with a plain numpy result array (the reference's return type): one more host copy")),
             gpu_launches=int(launches),
             roofline=dict(bound="tensor",
-                          kernel=("tc_conv_kernel: the 29 generator launches of one step (+ conv_post, 1 % of the stage time)" if args.precision != "fp32"
-                                  else "conv1d_nwc_kernel: the 29 generator launches of one step (+ conv_post)"),
+                          kernel=("tcgen05 conv kernels of the generator (tc_conv_kernel + tc_pair_ts_kernel), all launches of one step (+ conv_post, 1 % of the stage time)"
+                                  if args.precision != "fp32" else "conv1d_nwc_kernel: the generator launches of one step (+ conv_post)"),
                           achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_tflops_sustained"],
-                          traffic=traffic, traffic_unit="bytes of DRAM traffic per step, all launches of the kernel (ncu, profiles/r1_traffic.json)",
+                          traffic=traffic, traffic_source=traffic_src,
                           algorithmic_flops_per_step=flops, launch_ms=hg_ms,
                           frac_of_mode_ceiling=ach / ceiling,
                           mode_ceiling=("1/3 of the bf16 peak: bf16x3 issues three bf16 MMAs per algorithmic product" if args.precision != "fp32"
@@ -424,7 +624,9 @@ def run_ours(args):
                           peak_source=pk["source"] + ", sustained bf16 dense",
                           note=("algorithmic fp32 FLOPs; the bf16x3 path issues 3 bf16 MMAs per algorithmic product, so 1/3 of the bf16 peak is its ceiling"
                                 if args.precision != "fp32" else "strict-fp32 path runs on the FP32 FMA pipe (nominal 74 TFLOP/s)")),
+            roofline_stages=stages,
             clocks=clocks, weights=dict(bytes=wbytes, broadcast_s=t_w), melspec=mel_info, callers=callers,
+            sweep=sweep, strict_fp32=strict, configs=configs or None,
         )
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(synthetic.hifigan_params(1234), synthetic.acoustic_ckpt(1234), args.phonemes, args.seconds)
@@ -443,9 +645,15 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--phonemes", type=int, default=100)
     ap.add_argument("--seconds", type=float, default=5.0)
-    ap.add_argument("--ref-rows", type=int, default=1, help="utterances per step of the CPU reference arm")
+    ap.add_argument("--ref-rows", type=int, default=32, help="utterances per step of the CPU reference arm (default: the GPU arm's batch)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-callers", action="store_true", help="skip the duration/tts/gta/streaming side measurements (profiling runs)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep and the strict-fp32 line")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[3] / configs[4]")
+    ap.add_argument("--c5-rows", type=int, default=16, help="largest bucket of the mixed-length workload")
+    ap.add_argument("--pairs", default="auto", choices=["auto", "off", "tmem", "smem"],
+                    help="C<=64 ResBlock pairs: auto = library default, off = two conv launches per pair, tmem / smem = fused pair kernel "
+                         "with the A operand in tensor memory / shared memory")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"],
                     help="conv arithmetic: bf16x3 = tcgen05 split-bf16 with fp32 accumulate (default), fp32 = FMA pipe")
     args = ap.parse_args()

@@ -44,7 +44,8 @@ typedef enum vtts_status {
   VTTS_ERR_CUDA = -2,
   VTTS_ERR_NOT_LOADED = -3,   /* weights for this stage were not loaded */
   VTTS_ERR_NO_DEVICE = -4,    /* no CUDA device / not an sm_100 part */
-  VTTS_ERR_OOM = -5
+  VTTS_ERR_OOM = -5,
+  VTTS_ERR_NCCL = -6          /* NCCL missing or a collective failed (vtts_broadcast_weights) */
 } vtts_status;
 
 /* dropout handling for the prenet (vietTTS/nat/model.py:95-100: dropout is live at inference) */
@@ -81,6 +82,14 @@ int64_t vtts_duration_blob_floats(void);                 /* TokenEncoder block o
 int vtts_load_hifigan(vtts_ctx* ctx, const float* blob, int64_t n_floats);
 int vtts_load_acoustic(vtts_ctx* ctx, const float* blob, int64_t n_floats);
 int vtts_load_duration(vtts_ctx* ctx, const float* blob, int64_t n_floats);
+/* The one collective of the path: rank `root` has loaded its weights (vtts_load_*), every other rank
+ * receives the same models -- whichever of hifigan / acoustic / duration the root holds -- by ONE grouped ncclBroadcast
+ * of the device arenas and derives its packed tensor-core copies locally; no host round trip, nothing on the hot path
+ * afterwards.  `nccl_comm` is an ncclComm_t (passed as void*) whose rank on this process's device matches ctx; `is_root`
+ * != 0 on the root rank; `stream` a cudaStream_t or NULL.  Replaces the per-process pickle.load of the reference
+ * (hifigan/mel2wave.py:35-36, nat/text2mel.py:62-71) on ranks != root.  NCCL is bound with dlopen at the first call
+ * (libnccl.so.2 already in the process, else the loader path, else $VTTS_NCCL_LIB); VTTS_ERR_NCCL if that fails. */
+int vtts_broadcast_weights(vtts_ctx* ctx, void* nccl_comm, int root, int is_root, void* stream);
 /* librosa-style filterbank [80][513] (MelFilter.__init__, dsp.py:107-113) */
 int vtts_load_mel_filterbank(vtts_ctx* ctx, const float* fb, int n_mels, int n_bins);
 

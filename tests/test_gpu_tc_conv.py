@@ -95,10 +95,13 @@ def _ref_pair(x, w1, b1, w2, b2, k, dil, slope):
     return (y.transpose(1, 2) + xt).numpy()
 
 
+@pytest.mark.parametrize("ts", [True, False], ids=["tmem-operand", "smem-operand"])
 @pytest.mark.parametrize("C", [32, 64])
 @pytest.mark.parametrize("k,dil", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
-def test_fused_pair_vs_float64(eng, C, k, dil):
-    """Fused ResBlock pair (tc_pair.cu): row semantics (zero padding of BOTH convs at each row's true end)."""
+def test_fused_pair_vs_float64(eng, C, k, dil, ts):
+    """Fused ResBlock pair (tc_pair_ts.cu: A operand in tensor memory; tc_pair.cu: A operand in shared memory):
+    row semantics (zero padding of BOTH convs at each row's true end)."""
+    eng.set_fused_pairs(False, ts=ts)        # selects which pair kernel the debug hook runs; generator path unchanged
     rng = np.random.default_rng(C * 1000 + k * 10 + dil)
     B, T = 3, 700
     x = rng.standard_normal((B, T, C)).astype(np.float32)
@@ -117,12 +120,34 @@ def test_fused_pair_vs_float64(eng, C, k, dil):
         assert err < 3e-4, (C, k, dil, bb, err)
 
 
-def test_fused_and_unfused_generator_agree(eng, hifigan_params):
+@pytest.mark.parametrize("ts", [True, False], ids=["tmem-operand", "smem-operand"])
+def test_fused_and_unfused_generator_agree(eng, hifigan_params, ts):
     mel = synthetic.mel_input(21, 2, 50)
     nf = np.array([50, 31], np.int32)
-    eng.set_fused_pairs(True)
+    eng.set_fused_pairs(True, ts=ts)
     a = eng.mel2wave(mel, n_frames=nf)
     eng.set_fused_pairs(False)
     b = eng.mel2wave(mel, n_frames=nf)
-    eng.set_fused_pairs(True)
     assert np.abs(a - b).max() < 1e-4
+
+
+def test_fused_pair_long_rows_many_tiles(eng):
+    """More tiles than SMs (the persistent loop wraps, every ring changes phase many times) and a length that ends
+    inside a tile; C = 32 and 64 at the generator's own kernel sizes."""
+    eng.set_fused_pairs(False, ts=True)
+    dev = torch.device("cuda", 0)
+    for C, k, dil in ((32, 7, 3), (64, 11, 5), (64, 3, 1)):
+        rng = np.random.default_rng(C + k)
+        B, T = 4, 9000
+        x = rng.standard_normal((B, T, C)).astype(np.float32)
+        w1 = (rng.standard_normal((k, C, C)) / np.sqrt(k * C)).astype(np.float32)
+        w2 = (rng.standard_normal((k, C, C)) / np.sqrt(k * C)).astype(np.float32)
+        b1 = (rng.standard_normal(C) * 0.1).astype(np.float32)
+        b2 = (rng.standard_normal(C) * 0.1).astype(np.float32)
+        lens = np.array([T, 8191, 4097, 130], np.int32)
+        t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+        out = eng.debug_pair(t(x), t(w1), t(b1), t(w2), t(b2), k, dil, 0.1, t(lens)).cpu().numpy()
+        for bb in range(B):
+            n = lens[bb]
+            ref = _ref_pair(x[bb : bb + 1, :n], w1, b1, w2, b2, k, dil, 0.1)
+            assert np.abs(out[bb, :n] - ref[0]).max() < 3e-4, (C, k, dil, bb)

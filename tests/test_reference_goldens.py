@@ -99,3 +99,21 @@ def test_gta_teacher_forced_matches_reference_source(ack):
     mel1, mel2 = nat_oracle.teacher_forced(ack, z["tokens"], z["lengths"], frames, inp, keep, zone, dtype=torch.float64)
     assert np.abs(mel1 - z["mel1"]).max() < TOL * 10
     assert np.abs(mel2 - z["mel2"]).max() < TOL * 10
+
+
+def test_product_mask_stream_equals_the_masks_the_reference_drew():
+    """viettts_b200.jaxrng (what the drop-in predict_mel / GTA forward_fn feed the device by default) against the
+    masks recorded while the reference's own code drew them from the checkpoint rng (hk.next_rng_key chain +
+    jax.random.bernoulli, executed through tests/refshim)."""
+    from viettts_b200 import jaxrng
+    z = np.load(G / "nat_ref_predict_mel.npz")
+    keep = unpack(z, "keep")
+    assert np.array_equal(jaxrng.inference_keep_masks(z["rng"], 1, keep.shape[1]), keep)
+    z = np.load(G / "nat_ref_inference_b2.npz")
+    keep = unpack(z, "keep")
+    assert np.array_equal(jaxrng.inference_keep_masks(z["rng"], 2, keep.shape[1]), keep)      # [B,256] draws of a batched call
+    z = np.load(G / "nat_ref_gta.npz")
+    keep, zone = unpack(z, "keep"), unpack(z, "zone")
+    k2, z2 = jaxrng.teacher_forced_masks(z["rng"], keep.shape[0], keep.shape[1])
+    assert np.array_equal(k2, keep) and np.array_equal(z2, zone)
+    assert 0.08 < zone.mean() < 0.12 and 0.45 < keep.mean() < 0.55

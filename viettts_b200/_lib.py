@@ -40,6 +40,7 @@ SIGNATURES = {
     "vtts_predict_duration_host": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtts_load_acoustic": (C.c_int, [c_ctx, C.c_void_p, C.c_int64]),
     "vtts_load_mel_filterbank": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int]),
+    "vtts_broadcast_weights": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtts_hifigan_forward": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vtts_acoustic_forward": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 
+#include <dlfcn.h>
+
 #include "vtts_internal.cuh"
 
 std::string g_vtts_create_error;
@@ -154,17 +156,14 @@ static int64_t total_floats(const std::vector<TensorSpec>& s) {
 }
 
 // copy a contiguous blob (host or device) into per-tensor 256B-aligned device slots
-static int load_blob(vtts_ctx* ctx, const std::vector<TensorSpec>& specs, const float* blob, int64_t n_floats, float** store,
-                     std::vector<float*>& ptrs) {
-  if (!blob) return ctx->fail(VTTS_ERR_BAD_ARG, "load: null blob");
-  if (n_floats != total_floats(specs))
-    return ctx->fail(VTTS_ERR_BAD_ARG, "load: blob has %lld floats, expected %lld", (long long)n_floats, (long long)total_floats(specs));
+// device arena of one model: every tensor of `specs` 256 B aligned; returns the arena size in floats
+static size_t arena_floats(const std::vector<TensorSpec>& specs) {
   size_t total = 0;
-  std::vector<size_t> offs(specs.size());
-  for (size_t i = 0; i < specs.size(); ++i) {
-    offs[i] = total;
-    total += ((size_t)specs[i].n + 63) & ~size_t(63);
-  }
+  for (size_t i = 0; i < specs.size(); ++i) total += ((size_t)specs[i].n + 63) & ~size_t(63);
+  return total;
+}
+static int alloc_arena(vtts_ctx* ctx, const std::vector<TensorSpec>& specs, float** store, std::vector<float*>& ptrs) {
+  const size_t total = arena_floats(specs);
   if (*store) {
     VTTS_CUDA(cudaDeviceSynchronize());
     cudaFree(*store);
@@ -173,14 +172,59 @@ static int load_blob(vtts_ctx* ctx, const std::vector<TensorSpec>& specs, const 
   VTTS_CUDA(cudaMalloc(store, total * sizeof(float)));
   VTTS_CUDA(cudaMemset(*store, 0, total * sizeof(float)));
   ptrs.resize(specs.size());
+  size_t off = 0;
+  for (size_t i = 0; i < specs.size(); ++i) {
+    ptrs[i] = *store + off;
+    off += ((size_t)specs[i].n + 63) & ~size_t(63);
+  }
+  return VTTS_OK;
+}
+static int load_blob(vtts_ctx* ctx, const std::vector<TensorSpec>& specs, const float* blob, int64_t n_floats, float** store,
+                     std::vector<float*>& ptrs) {
+  if (!blob) return ctx->fail(VTTS_ERR_BAD_ARG, "load: null blob");
+  if (n_floats != total_floats(specs))
+    return ctx->fail(VTTS_ERR_BAD_ARG, "load: blob has %lld floats, expected %lld", (long long)n_floats, (long long)total_floats(specs));
+  int rc = alloc_arena(ctx, specs, store, ptrs);
+  if (rc) return rc;
   int64_t src = 0;
   for (size_t i = 0; i < specs.size(); ++i) {
-    ptrs[i] = *store + offs[i];
     VTTS_CUDA(cudaMemcpy(ptrs[i], blob + src, (size_t)specs[i].n * sizeof(float), cudaMemcpyDefault));
     src += specs[i].n;
   }
   return VTTS_OK;
 }
+
+// ---- NCCL, bound at run time (the library has no link-time dependency on it: single-GPU users never load it) ----
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const char* nccl_bind() {
+  if (g_nccl.Broadcast) return nullptr;
+  const char* env = getenv("VTTS_NCCL_LIB");
+  void* h = nullptr;
+  if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);        // the copy the host process (e.g. torch) already loaded
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return "libnccl.so.2 not found (set VTTS_NCCL_LIB to its path)";
+  g_nccl.h = h;
+  g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(h, "ncclBroadcast");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+    g_nccl.Broadcast = nullptr;
+    return "libnccl.so.2 lacks ncclBroadcast / ncclGroupStart / ncclGroupEnd";
+  }
+  return nullptr;
+}
+}  // namespace
 
 extern "C" {
 
@@ -306,6 +350,7 @@ int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16) {
   VTTS_CUDA(cudaMemset(ctx->d_tc_dbg, 0, 256 * 16 * sizeof(long long)));
   ctx->tc_dbg_on = (enable & 1) != 0;
   if (enable & 0x200) ctx->fuse_pairs = (enable >> 10) & 1;        // bit 9 set: bit 10 selects fused ResBlock pairs (tuning aid)
+  if (enable & 0x800) ctx->pair_ts = (enable >> 12) & 1;           // bit 11 set: bit 12 selects the TS (A in TMEM) pair kernel
   if (enable & 0x100) ctx->tc_variant = (enable >> 4) & 0xF;   // bit 8 set: bits 4..7 select the tile-shape variant (tuning aid)
   return VTTS_OK;
 }
@@ -404,6 +449,58 @@ int vtts_load_duration(vtts_ctx* ctx, const float* blob, int64_t n_floats) {
   rc = vtts_duration_prepare(ctx);
   if (rc) return rc;
   ctx->du_loaded = true;
+  return VTTS_OK;
+}
+
+// One start-up broadcast of the packed weights from `root` (the only collective of the path).
+int vtts_broadcast_weights(vtts_ctx* ctx, void* nccl_comm, int root, int is_root, void* stream) {
+  if (!ctx) return VTTS_ERR_BAD_ARG;
+  if (!nccl_comm) return ctx->fail(VTTS_ERR_BAD_ARG, "broadcast_weights: null communicator");
+  VTTS_CUDA(cudaSetDevice(ctx->device));
+  if (const char* e = nccl_bind()) return ctx->fail(VTTS_ERR_NCCL, "broadcast_weights: %s", e);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto nccl_ck = [&](int r, const char* what) -> int {
+    if (r == 0) return VTTS_OK;
+    return ctx->fail(VTTS_ERR_NCCL, "broadcast_weights: %s -> %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
+  };
+  // which models travel: bit 0 hifigan, 1 acoustic, 2 duration (decided by the root's loaded state)
+  int32_t* d_flags = nullptr;
+  VTTS_CUDA(cudaMalloc(&d_flags, sizeof(int32_t)));
+  int32_t flags = is_root ? ((ctx->hg_loaded ? 1 : 0) | (ctx->ac_loaded ? 2 : 0) | (ctx->du_loaded ? 4 : 0)) : 0;
+  VTTS_CUDA(cudaMemcpyAsync(d_flags, &flags, sizeof(flags), cudaMemcpyHostToDevice, st));
+  int rc = nccl_ck(g_nccl.Broadcast(d_flags, d_flags, 1, /*ncclInt32*/ 2, root, nccl_comm, st), "ncclBroadcast(flags)");
+  if (rc) { cudaFree(d_flags); return rc; }
+  VTTS_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_flags);
+  if (is_root && flags == 0) return ctx->fail(VTTS_ERR_NOT_LOADED, "broadcast_weights: the root context has no weights loaded");
+  struct M { int bit; const std::vector<TensorSpec>* specs; float** store; std::vector<float*>* ptrs; bool* loaded; };
+  M models[3] = {{1, &vtts_hifigan_specs(), &ctx->hg_blob, &ctx->hg_t, &ctx->hg_loaded},
+                 {2, &vtts_acoustic_specs(), &ctx->ac_blob, &ctx->ac_t, &ctx->ac_loaded},
+                 {4, &vtts_duration_specs(), &ctx->du_blob, &ctx->du_t, &ctx->du_loaded}};
+  if (!is_root)
+    for (auto& m : models)
+      if (flags & m.bit) {
+        *m.loaded = false;
+        rc = alloc_arena(ctx, *m.specs, m.store, *m.ptrs);
+        if (rc) return rc;
+      }
+  // the arenas have the same layout on every rank (it only depends on the tensor specs): ONE grouped broadcast
+  rc = nccl_ck(g_nccl.GroupStart(), "ncclGroupStart");
+  if (rc) return rc;
+  for (auto& m : models)
+    if (flags & m.bit) {
+      rc = nccl_ck(g_nccl.Broadcast(*m.store, *m.store, arena_floats(*m.specs), /*ncclFloat32*/ 7, root, nccl_comm, st), "ncclBroadcast(weights)");
+      if (rc) { g_nccl.GroupEnd(); return rc; }
+    }
+  rc = nccl_ck(g_nccl.GroupEnd(), "ncclGroupEnd");
+  if (rc) return rc;
+  VTTS_CUDA(cudaStreamSynchronize(st));
+  if (!is_root) {
+    if (flags & 1) { rc = vtts_hifigan_prepare(ctx); if (rc) return rc; ctx->hg_loaded = true; }
+    if (flags & 2) { rc = vtts_acoustic_prepare(ctx); if (rc) return rc; ctx->ac_loaded = true; }
+    if (flags & 4) { rc = vtts_duration_prepare(ctx); if (rc) return rc; ctx->du_loaded = true; }
+  }
   return VTTS_OK;
 }
 

@@ -144,6 +144,7 @@ struct vtts_ctx {
   long long* d_tc_dbg = nullptr;   // [256][16] profiling counters of the last tensor-core conv launch
   bool tc_dbg_on = false;
   int fuse_pairs = 0;              // 1 = ResBlock pairs with C <= 64 run in the fused tc_pair kernel (cuts HBM traffic 2.5x but is MMA-issue bound: off by default)
+  int pair_ts = 1;                 // fused pairs use the TS kernel (tc_pair_ts.cu); 0 = the shared-memory-operand kernel (tc_pair.cu)
   int tc_variant = 1;              // tile-shape variant of the tensor-core conv (see TcCfg); 1 = double-buffered accumulators for N >= 128
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
@@ -251,7 +252,9 @@ size_t vtts_tc_packed_elems(int k, int Cin, int N);
 int vtts_tc_pack_weights(vtts_ctx* ctx, const float* w, void* dst, int k, int Cin, int Cout_total, int n0, int N);
 int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st);
 // tc_pair.cu
-int vtts_launch_tc_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);
+int vtts_launch_tc_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);   // dispatches on ctx->pair_ts
+// tc_pair_ts.cu: same operator with the A operand in tensor memory (TS form of tcgen05.mma)
+int vtts_launch_tc_pair_ts(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);
 // generic dispatch: runs `L` on the tensor-core path when ctx->precision == 1 and packed weights are given
 // (wpk[prob * ntile + tile], ntile = ceil(Cout/256) tiles of width vtts_tc_tile_n(Cout)), else on the FP32 path
 int vtts_tc_tile_n(int Cout);

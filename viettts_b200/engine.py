@@ -108,9 +108,10 @@ class Engine:
                                           B, T, Cc, int(k), int(dil), float(slope), _ptr(out)))
         return out
 
-    def set_fused_pairs(self, on: bool):
-        """Run the C <= 64 ResBlock pairs in the fused tc_pair kernel (default: two tensor-core conv launches)."""
-        self._ck(self.lib.vtts_debug_tc_stats(self.h, 0x200 | ((1 if on else 0) << 10), None))
+    def set_fused_pairs(self, on: bool, ts: bool = True):
+        """Run the C <= 64 ResBlock pairs in a fused pair kernel (off: two tensor-core conv launches per pair).
+        ts=True: tc_pair_ts.cu (A operand in tensor memory); ts=False: tc_pair.cu (A operand in shared memory)."""
+        self._ck(self.lib.vtts_debug_tc_stats(self.h, 0x200 | ((1 if on else 0) << 10) | 0x800 | ((1 if ts else 0) << 12), None))
 
     def tc_stats(self, enable=True, variant=None):
         """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats);
@@ -159,6 +160,13 @@ class Engine:
             blob = _np(blob, np.float32)
         self._ck(self.lib.vtts_load_duration(self.h, _ptr(blob), n))
         self._duration_key = key if key is not None else object()
+
+    def broadcast_weights(self, nccl_comm, root: int, is_root: bool, stream=None):
+        """vtts_broadcast_weights: the root's loaded models reach every rank's context by one grouped ncclBroadcast.
+        `nccl_comm`: an ncclComm_t as ctypes.c_void_p / int (e.g. parallel.NcclComm(...).handle)."""
+        self._ck(self.lib.vtts_broadcast_weights(self.h, nccl_comm, int(root), 1 if is_root else 0, stream))
+        if not is_root:
+            self._hifigan_key = self._acoustic_key = self._duration_key = object()
 
     def load_mel_filterbank(self, fb=None):
         fb = _np(weights.mel_filterbank() if fb is None else fb, np.float32, (config.MEL_DIM, config.N_FFT // 2 + 1), "filterbank")

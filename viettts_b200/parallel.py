@@ -90,3 +90,72 @@ def load_weights_distributed(engine, hifigan_params=None, acoustic_ckpt=None, de
         engine.load_duration(dt)
         total += dt.numel() * 4
     return total
+
+
+# ---------------------------------------------------------------------------------------------------------
+# start-up broadcast through the C ABI (vtts_broadcast_weights): for hosts that are not Python / torch the ABI call
+# is the whole story (they hand in their own ncclComm_t); this helper builds a communicator for the torch case.
+# ---------------------------------------------------------------------------------------------------------
+class NcclComm:
+    """A raw ncclComm_t over the ranks of the initialised torch.distributed group, created with ctypes on the libnccl
+    the process already has loaded (torch's bundled copy).  The unique id travels through torch.distributed."""
+
+    def __init__(self, device_index: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+
+        path = None
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl.so" in line:
+                    path = line.split()[-1]
+                    break
+        self.lib = C.CDLL(path or "libnccl.so.2")
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]
+
+        self.lib.ncclGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = UniqueId()
+        if rank == 0:
+            rc = self.lib.ncclGetUniqueId(C.byref(uid))
+            if rc != 0:
+                raise RuntimeError(f"ncclGetUniqueId -> {rc}")
+        box = [bytes(uid.internal)] if rank == 0 else [None]
+        # bytes() of a c_char array stops at the first NUL: ship the raw buffer instead
+        box = [C.string_at(C.addressof(uid), 128)] if rank == 0 else [None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        C.memmove(C.addressof(uid), box[0], 128)
+        torch.cuda.set_device(device_index)
+        comm = C.c_void_p()
+        rc = self.lib.ncclCommInitRank(C.byref(comm), world, uid, rank)
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank -> {rc}")
+        self.handle = comm
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ncclCommDestroy(self.handle)
+            self.handle = None
+
+
+def load_weights_via_abi(engine, hifigan_params=None, acoustic_ckpt=None, duration_ckpt=None, src: int = 0, group=None):
+    """Rank `src` loads the Haiku-layout checkpoints into its context; every other rank receives them by
+    vtts_broadcast_weights (one grouped ncclBroadcast of the device arenas).  Returns the NcclComm (keep or close)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    if rank == src:
+        if hifigan_params is not None:
+            engine.load_hifigan(hifigan_params)
+        if acoustic_ckpt is not None:
+            engine.load_acoustic(acoustic_ckpt)
+        if duration_ckpt is not None:
+            engine.load_duration(duration_ckpt)
+    comm = NcclComm(engine.device, group)
+    engine.broadcast_weights(comm.handle, src, rank == src)
+    return comm
