@@ -374,8 +374,10 @@ def run_ours(args):
 
     eng = Engine(local)
     eng.set_precision(args.precision)
+    if args.tc_variant is not None:
+        eng.tc_stats(False, variant=args.tc_variant)
     if args.pairs != "auto":
-        eng.set_fused_pairs(args.pairs != "off", ts=args.pairs != "smem")
+        eng.set_fused_pairs(args.pairs != "off", kind=None if args.pairs == "off" else args.pairs)
     hp = synthetic.hifigan_params(1234) if rank == 0 else None
     ck = synthetic.acoustic_ckpt(1234) if rank == 0 else None
     t_w = time.perf_counter()
@@ -651,9 +653,10 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep and the strict-fp32 line")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[3] / configs[4]")
     ap.add_argument("--c5-rows", type=int, default=16, help="largest bucket of the mixed-length workload")
-    ap.add_argument("--pairs", default="auto", choices=["auto", "off", "tmem", "smem"],
+    ap.add_argument("--pairs", default="auto", choices=["auto", "off", "smem2", "tmem", "smem"],
                     help="C<=64 ResBlock pairs: auto = library default, off = two conv launches per pair, tmem / smem = fused pair kernel "
                          "with the A operand in tensor memory / shared memory")
+    ap.add_argument("--tc-variant", type=int, default=None, help="tile-shape variant of tc_conv (tuning aid; default: library default)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"],
                     help="conv arithmetic: bf16x3 = tcgen05 split-bf16 with fp32 accumulate (default), fp32 = FMA pipe")
     args = ap.parse_args()

@@ -34,11 +34,11 @@ for C, k, dil, rows in [(64, 3, 1, 1_277_952), (64, 7, 3, 1_277_952), (64, 11, 5
     b2 = torch.randn(C, device=dev) * 0.1
     flops = 2 * 2.0 * rows * C * C * k
     res = {}
-    for name, ts in (("tmem", True), ("smem", False)):
-        eng.set_fused_pairs(False, ts=ts)
+    for name in ("smem2", "tmem", "smem"):
+        eng.set_fused_pairs(False, kind=name)
         # debug_pair packs the weights on every call (cudaMalloc + pack kernel): subtract a k=1-sized call? no -- report it as is,
         # the pack kernels are ~20 us
         res[name] = timed(lambda: eng.debug_pair(x, w1, b1, w2, b2, k, dil))
     t2 = timed(lambda: (eng.debug_conv1d("bf16x3", x, w1, b1, k, dil, 0.1), eng.debug_conv1d("bf16x3", x, w2, b2, k, 1, 0.1, resid_t=x)))
-    print(f"pair C={C} k={k:2d} d={dil}: tmem-operand {res['tmem']:.3f} ms ({flops/res['tmem']/1e9:.0f} TFLOP/s alg) | smem-operand {res['smem']:.3f} ms "
+    print(f"pair C={C} k={k:2d} d={dil}: pair2 {res['smem2']:.3f} ms ({flops/res['smem2']/1e9:.0f} TFLOP/s alg) | tmem-operand {res['tmem']:.3f} ({flops/res['tmem']/1e9:.0f}) | pair1 {res['smem']:.3f} "
           f"({flops/res['smem']/1e9:.0f}) | two launches {t2:.3f} ms ({flops/t2/1e9:.0f})", flush=True)

@@ -95,13 +95,13 @@ def _ref_pair(x, w1, b1, w2, b2, k, dil, slope):
     return (y.transpose(1, 2) + xt).numpy()
 
 
-@pytest.mark.parametrize("ts", [True, False], ids=["tmem-operand", "smem-operand"])
+@pytest.mark.parametrize("ts", ["smem2", "tmem", "smem"])
 @pytest.mark.parametrize("C", [32, 64])
 @pytest.mark.parametrize("k,dil", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
 def test_fused_pair_vs_float64(eng, C, k, dil, ts):
     """Fused ResBlock pair (tc_pair_ts.cu: A operand in tensor memory; tc_pair.cu: A operand in shared memory):
     row semantics (zero padding of BOTH convs at each row's true end)."""
-    eng.set_fused_pairs(False, ts=ts)        # selects which pair kernel the debug hook runs; generator path unchanged
+    eng.set_fused_pairs(False, kind=ts)      # selects which pair kernel the debug hook runs; generator path unchanged
     rng = np.random.default_rng(C * 1000 + k * 10 + dil)
     B, T = 3, 700
     x = rng.standard_normal((B, T, C)).astype(np.float32)
@@ -120,11 +120,11 @@ def test_fused_pair_vs_float64(eng, C, k, dil, ts):
         assert err < 3e-4, (C, k, dil, bb, err)
 
 
-@pytest.mark.parametrize("ts", [True, False], ids=["tmem-operand", "smem-operand"])
+@pytest.mark.parametrize("ts", ["smem2", "tmem", "smem"])
 def test_fused_and_unfused_generator_agree(eng, hifigan_params, ts):
     mel = synthetic.mel_input(21, 2, 50)
     nf = np.array([50, 31], np.int32)
-    eng.set_fused_pairs(True, ts=ts)
+    eng.set_fused_pairs(True, kind=ts)
     a = eng.mel2wave(mel, n_frames=nf)
     eng.set_fused_pairs(False)
     b = eng.mel2wave(mel, n_frames=nf)
@@ -134,9 +134,9 @@ def test_fused_and_unfused_generator_agree(eng, hifigan_params, ts):
 def test_fused_pair_long_rows_many_tiles(eng):
     """More tiles than SMs (the persistent loop wraps, every ring changes phase many times) and a length that ends
     inside a tile; C = 32 and 64 at the generator's own kernel sizes."""
-    eng.set_fused_pairs(False, ts=True)
     dev = torch.device("cuda", 0)
-    for C, k, dil in ((32, 7, 3), (64, 11, 5), (64, 3, 1)):
+    for kind, C, k, dil in (("smem2", 32, 7, 3), ("smem2", 64, 11, 5), ("smem2", 64, 3, 1), ("tmem", 32, 11, 5), ("tmem", 64, 7, 3)):
+        eng.set_fused_pairs(False, kind=kind)
         rng = np.random.default_rng(C + k)
         B, T = 4, 9000
         x = rng.standard_normal((B, T, C)).astype(np.float32)

@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libviettts_b200.so"
-SOURCES = ["api.cu", "conv1d.cu", "tc_conv.cu", "tc_pair.cu", "tc_pair_ts.cu", "hifigan.cu", "nat.cu", "melspec.cu"]
+SOURCES = ["api.cu", "conv1d.cu", "tc_conv.cu", "tc_pair.cu", "tc_pair_ts.cu", "tc_pair2.cu", "hifigan.cu", "nat.cu", "melspec.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -350,7 +350,7 @@ int vtts_debug_tc_stats(vtts_ctx* ctx, int enable, int64_t* host_out_256x16) {
   VTTS_CUDA(cudaMemset(ctx->d_tc_dbg, 0, 256 * 16 * sizeof(long long)));
   ctx->tc_dbg_on = (enable & 1) != 0;
   if (enable & 0x200) ctx->fuse_pairs = (enable >> 10) & 1;        // bit 9 set: bit 10 selects fused ResBlock pairs (tuning aid)
-  if (enable & 0x800) ctx->pair_ts = (enable >> 12) & 1;           // bit 11 set: bit 12 selects the TS (A in TMEM) pair kernel
+  if (enable & 0x800) ctx->pair_ts = (enable >> 12) & 3;           // bit 11 set: bits 12..13 select the pair kernel (vtts_ctx::pair_ts)
   if (enable & 0x100) ctx->tc_variant = (enable >> 4) & 0xF;   // bit 8 set: bits 4..7 select the tile-shape variant (tuning aid)
   return VTTS_OK;
 }

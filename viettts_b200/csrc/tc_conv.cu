@@ -473,6 +473,8 @@ int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
     if (nph == 4) return launch_cfg<128, EPI, 1, 4>(ctx, L, st);
     if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=128 supports 1 or 4 phases");
     if (ctx->tc_variant == 0) return launch_cfg<128, EPI, 4, 1>(ctx, L, st);
+    // stacked [W_hi | W_lo]: two MMAs (N' = 256, then N' = 128) instead of three of N' = 128 per (chunk, tap, M tile)
+    if (ctx->tc_variant == 2) return launch_cfg<128, EPI, 1, 1, 1>(ctx, L, st);
     return launch_cfg<128, EPI, 2, 1>(ctx, L, st);
   } else if constexpr (N == 64) {
     if (nph == 2) return launch_cfg<64, EPI, 2, 2>(ctx, L, st);

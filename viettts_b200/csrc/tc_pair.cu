@@ -418,7 +418,8 @@ int launch_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
 }  // namespace
 
 int vtts_launch_tc_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
-  if (ctx->pair_ts) return vtts_launch_tc_pair_ts(ctx, L, st);
+  if (ctx->pair_ts == 1) return vtts_launch_tc_pair_ts(ctx, L, st);
+  if (ctx->pair_ts == 2) return vtts_launch_tc_pair2(ctx, L, st);
   if (L.nprob < 1 || L.nprob > 3) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_pair: nprob %d", L.nprob);
   for (int i = 0; i < L.nprob; ++i) {
     const TcPairProb& p = L.p[i];

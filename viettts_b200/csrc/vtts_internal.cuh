@@ -143,8 +143,8 @@ struct vtts_ctx {
   int* d_err = nullptr;
   long long* d_tc_dbg = nullptr;   // [256][16] profiling counters of the last tensor-core conv launch
   bool tc_dbg_on = false;
-  int fuse_pairs = 0;              // 1 = ResBlock pairs with C <= 64 run in the fused tc_pair kernel (cuts HBM traffic 2.5x but is MMA-issue bound: off by default)
-  int pair_ts = 1;                 // fused pairs use the TS kernel (tc_pair_ts.cu); 0 = the shared-memory-operand kernel (tc_pair.cu)
+  int fuse_pairs = 1;              // 1 = ResBlock pairs with C <= 64 run in a fused pair kernel (intermediate stays on chip: 8 instead of 20 B of HBM traffic per element pair)
+  int pair_ts = 2;                 // fused pair kernel: 0 tc_pair.cu (one issuer, smem operand), 1 tc_pair_ts.cu (operand in TMEM), 2 tc_pair2.cu (two decoupled pipelines, smem operand)
   int tc_variant = 1;              // tile-shape variant of the tensor-core conv (see TcCfg); 1 = double-buffered accumulators for N >= 128
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
@@ -255,6 +255,8 @@ int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st);
 int vtts_launch_tc_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);   // dispatches on ctx->pair_ts
 // tc_pair_ts.cu: same operator with the A operand in tensor memory (TS form of tcgen05.mma)
 int vtts_launch_tc_pair_ts(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);
+// tc_pair2.cu: shared-memory operand, conv1 / conv2 as two decoupled pipelines with one issuing warp each
+int vtts_launch_tc_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st);
 // generic dispatch: runs `L` on the tensor-core path when ctx->precision == 1 and packed weights are given
 // (wpk[prob * ntile + tile], ntile = ceil(Cout/256) tiles of width vtts_tc_tile_n(Cout)), else on the FP32 path
 int vtts_tc_tile_n(int Cout);

@@ -108,10 +108,16 @@ class Engine:
                                           B, T, Cc, int(k), int(dil), float(slope), _ptr(out)))
         return out
 
-    def set_fused_pairs(self, on: bool, ts: bool = True):
+    PAIR_KERNELS = {"smem": 0, "tmem": 1, "smem2": 2}
+
+    def set_fused_pairs(self, on: bool, ts=None, kind: str | None = None):
         """Run the C <= 64 ResBlock pairs in a fused pair kernel (off: two tensor-core conv launches per pair).
-        ts=True: tc_pair_ts.cu (A operand in tensor memory); ts=False: tc_pair.cu (A operand in shared memory)."""
-        self._ck(self.lib.vtts_debug_tc_stats(self.h, 0x200 | ((1 if on else 0) << 10) | 0x800 | ((1 if ts else 0) << 12), None))
+        kind: "smem2" tc_pair2.cu (two decoupled pipelines, A operand in shared memory; the default), "tmem"
+        tc_pair_ts.cu (A operand in tensor memory), "smem" tc_pair.cu (first generation).  `ts` is the old spelling
+        (True = "tmem", False = "smem")."""
+        if kind is None:
+            kind = "smem2" if ts is None else ("tmem" if ts else "smem")
+        self._ck(self.lib.vtts_debug_tc_stats(self.h, 0x200 | ((1 if on else 0) << 10) | 0x800 | (self.PAIR_KERNELS[kind] << 12), None))
 
     def tc_stats(self, enable=True, variant=None):
         """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats);
