@@ -125,7 +125,7 @@ def cpu_pick_threads(hp, ck):
     from oracle import hifigan_oracle, nat_oracle
     cores = os.cpu_count() or 1
     tokens, durs, nfs = make_batch(1, 20, 0.4, 7)
-    mel = synthetic.mel_input(1, 1, 24)
+    mel = synthetic.mel_input(1, 1, 96)               # long enough that the conv threading of a 5 s utterance shows
 
     def t_nat():
         with torch.no_grad():
@@ -136,7 +136,7 @@ def cpu_pick_threads(hp, ck):
             hifigan_oracle.generator_forward(hp, mel)
 
     best = {}
-    for name, fn, cands in (("nat", t_nat, [1, 2, 4, 8, 16]), ("hifigan", t_hg, [4, 8, 16, 32, 64, 128, cores])):
+    for name, fn, cands in (("nat", t_nat, [1, 2, 4, 8, 16]), ("hifigan", t_hg, [8, 16, 32, 64, cores])):
         res = []
         for n in sorted(set(c for c in cands if c <= cores)):
             torch.set_num_threads(n)
@@ -150,17 +150,21 @@ def cpu_pick_threads(hp, ck):
 
 
 def cpu_port_step(hp, ck, tokens, durs, nfs, masks):
-    """One pass of the reference algorithm (torch CPU restatement) over the given utterances."""
+    """One pass of the reference algorithm (torch CPU restatement) over the given utterances, one utterance per call
+    like the reference's own predict_mel / mel2wave (a 32-row call is slower per utterance on the host: its
+    activations, 135 MB per utterance, fall out of every cache)."""
     import torch
     from oracle import hifigan_oracle, nat_oracle
     th = cpu_pick_threads(hp, ck)
-    n = int(nfs[0])
+    total = 0
     with torch.no_grad():
-        torch.set_num_threads(th["nat"])
-        mel = nat_oracle.inference(ck, tokens, durs, n, masks)
-        torch.set_num_threads(th["hifigan"])
-        wav = hifigan_oracle.generator_forward(hp, mel.numpy())
-    return int(wav.numel())
+        for r in range(tokens.shape[0]):
+            torch.set_num_threads(th["nat"])
+            mel = nat_oracle.inference(ck, tokens[r:r + 1], durs[r:r + 1], int(nfs[r]), masks[r:r + 1])
+            torch.set_num_threads(th["hifigan"])
+            wav = hifigan_oracle.generator_forward(hp, mel.numpy())
+            total += int(wav.numel())
+    return total
 
 
 def cpu_baseline(hp, ck, phonemes, seconds, budget_s=12.0, rows=1):
@@ -193,15 +197,22 @@ def run_reference(args):
     rows = args.ref_rows
     tokens, durs, nfs = make_batch(rows, args.phonemes, args.seconds, 0)
     masks = synthetic.dropout_masks(3, rows, int(nfs[0]))
+    t0 = time.perf_counter()
     cpu_port_step(hp, ck, tokens[:1], durs[:1], nfs[:1], masks[:1])      # one warm-up pass (the CPU port has no compile / cache state to warm)
+    t_row = time.perf_counter() - t0
+    # bounded sample: keep the whole run near the budget (default 150 s) by trimming the rows of a step, never below one
+    cap = max(1, int(args.ref_budget_s / max(args.steps, 1) / max(t_row, 1e-3)))
+    if cap < rows:
+        rows = cap
+        tokens, durs, nfs, masks = tokens[:rows], durs[:rows], nfs[:rows], masks[:rows]
     t0 = time.perf_counter()
     samples = 0
     for _ in range(args.steps):
         samples += cpu_port_step(hp, ck, tokens, durs, nfs, masks)
     dt = time.perf_counter() - t0
     val = samples / dt
-    desc = (f"{args.steps} steps x {rows} utterance(s) through oracle/ (torch CPU restatement; threads: acoustic {th['nat']}, "
-            f"generator {th['hifigan']} of {os.cpu_count()} host threads)")
+    desc = (f"{args.steps} steps x {rows} utterance(s) of the batch-{args.batch} workload, one utterance per call, through oracle/ (torch CPU "
+            f"restatement; threads: acoustic {th['nat']}, generator {th['hifigan']} of {os.cpu_count()} host threads)")
     out = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                rtf=(dt / (samples / C.SAMPLE_RATE)),
@@ -648,6 +659,7 @@ def main():
     ap.add_argument("--phonemes", type=int, default=100)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--ref-rows", type=int, default=32, help="utterances per step of the CPU reference arm (default: the GPU arm's batch)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-time target of the whole reference-arm run; a step is trimmed to fewer rows if needed")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-callers", action="store_true", help="skip the duration/tts/gta/streaming side measurements (profiling runs)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep and the strict-fp32 line")

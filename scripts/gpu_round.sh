@@ -1,15 +1,15 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list. Outputs under gpurun_out/.
+# One GPU-box visit: parity tests, smoke, bench, (optional) ncu launch list. Outputs under gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest -m gpu"
-timeout 1200 python -m pytest tests -m gpu -x -q -s ${PYTEST_ARGS} 2>&1 | tail -${TAIL:-45} | tee gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_ARGS} 2>&1 | tail -${TAIL:-25} | tee gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
 echo "== bench"
-timeout 600 python bench.py --steps ${STEPS:-5} --warmup 3 ${BENCH_ARGS} 2>&1 | tail -2 | tee gpurun_out/bench.log
+timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ -n "$NCU" ]; then
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu ${BENCH_ARGS} > gpurun_out/ncu_bench.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-callers --no-sweep --no-configs ${BENCH_ARGS} > gpurun_out/ncu_bench.log 2>&1
 tail -1 gpurun_out/ncu_bench.log | cut -c1-200
 fi
