@@ -496,10 +496,9 @@ def run_ours(args):
         # ================= BASELINE configs[4]: n=256 mixed 50-300 phonemes, bucketed <= 8 % padding =================
         utts = c5_workload()
         nfs5 = [u[2] for u in utts]
-        buckets = parallel.bucket_by_length(nfs5, 0.08, max_rows=args.c5_rows)
-        # cost model of one bucket: the scan is paid per frame of its longest row, the generator per padded row-frame
-        cost = [int(max(nfs5[i] for i in bk) * (22.0 + 1.9 * len(bk))) for bk in buckets]
-        mine = parallel.lpt_shard(cost, world)[rank]
+        # equal-cost contiguous buckets (a multiple of the rank count), LPT-assigned: parallel.balanced_buckets
+        buckets, shards5 = parallel.balanced_buckets(nfs5, world, groups_per_rank=args.c5_groups or None, max_pad_frac=0.08, max_rows=32)
+        mine = shards5[rank]
         jobs5 = []
         for bi in mine:
             bk = buckets[bi]
@@ -516,7 +515,7 @@ def run_ours(args):
         padded = sum(len(bk) * max(nfs5[i] for i in bk) for bk in buckets)
         configs["c5"] = dict(workload="256 utterances, 50-300 phonemes (156-937 frames), bucketed by frame count and LPT-assigned to the ranks "
                                       "(BASELINE configs[4])", scaling="strong", n_utterances=len(utts), n_buckets=len(buckets),
-                             max_rows_per_bucket=args.c5_rows, padding_frac=1.0 - sum(nfs5) / padded, buckets_on_this_rank=len(mine), **r)
+                             buckets_per_rank=len(buckets) / world, rows_per_bucket=[len(bk) for bk in buckets], padding_frac=1.0 - sum(nfs5) / padded, buckets_on_this_rank=len(mine), **r)
         del jobs5
 
     # ================= per-stage rooflines (rank 0) =================
@@ -664,7 +663,7 @@ def main():
     ap.add_argument("--no-callers", action="store_true", help="skip the duration/tts/gta/streaming side measurements (profiling runs)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep and the strict-fp32 line")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[3] / configs[4]")
-    ap.add_argument("--c5-rows", type=int, default=16, help="largest bucket of the mixed-length workload")
+    ap.add_argument("--c5-groups", type=int, default=0, help="equal-cost buckets per rank of the mixed-length workload (0 = pick 2..4 by predicted makespan)")
     ap.add_argument("--pairs", default="auto", choices=["auto", "off", "smem2", "tmem", "smem"],
                     help="C<=64 ResBlock pairs: auto = library default, off = two conv launches per pair, tmem / smem = fused pair kernel "
                          "with the A operand in tensor memory / shared memory")

@@ -91,3 +91,24 @@ def test_duration_fixups(tokens, silence, seed):
     assert np.array_equal(out[0, rest], d[0, rest])
     frames, n = t2m.seconds_to_frames(out)
     assert n == int(np.sum(frames, dtype=np.float32)) and frames.dtype == np.float32
+
+
+def test_balanced_buckets_equal_cost_and_padding_bound():
+    """parallel.balanced_buckets (BASELINE configs[4]): every utterance placed exactly once, whole-workload padding within
+    the bound, at most 32 rows per bucket (one decoder scan), predicted per-rank cost within 5 % of the mean at 8 ranks."""
+    import numpy as np
+    from viettts_b200 import parallel
+    rng = np.random.default_rng(3)
+    for trial in range(5):
+        n = (rng.integers(50, 301, size=256) * 3.125).astype(np.int64)
+        for world in (1, 2, 8):
+            buckets, shards = parallel.balanced_buckets(n, world)
+            flat = sorted(i for b in buckets for i in b)
+            assert flat == list(range(len(n)))
+            assert sorted(i for s in shards for i in s) == list(range(len(buckets)))
+            assert max(len(b) for b in buckets) <= 32
+            padded = sum(len(b) * int(n[b].max()) for b in buckets)
+            assert 1.0 - n.sum() / padded <= 0.08
+            loads = [sum(parallel.batch_cost_us(n[buckets[i]]) for i in s) for s in shards]
+            if world == 8:
+                assert max(loads) / np.mean(loads) <= 1.05, (trial, world, max(loads) / np.mean(loads))

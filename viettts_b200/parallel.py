@@ -45,6 +45,73 @@ def bucket_by_length(n_frames, max_pad_frac: float = 0.08, max_rows: int = 128):
     return buckets
 
 
+# measured cost model of one ragged batch on a B200 (bench.py `roofline_stages`): the decoder scan is paid per frame of
+# the batch's longest row (sequential, ~20 us per frame for up to 32 rows), everything else per padded row-frame
+SCAN_US_PER_FRAME = 20.0
+ROW_US_PER_FRAME = 1.9
+
+
+def batch_cost_us(n_frames_of_rows) -> float:
+    n = np.asarray(n_frames_of_rows, dtype=np.int64)
+    scans = (len(n) + 31) // 32                       # the decoder scan takes up to 32 rows per launch
+    return float(n.max()) * (SCAN_US_PER_FRAME * scans + ROW_US_PER_FRAME * len(n))
+
+
+def balanced_buckets(n_frames, world_size: int, groups_per_rank=None, max_pad_frac: float = 0.08, max_rows: int = 32):
+    """Mixed-length workload (BASELINE configs[4]) for `world_size` ranks: utterances sorted by frame count are cut into
+    world_size * groups_per_rank CONTIGUOUS buckets of (nearly) equal predicted cost -- so a bucket of long utterances
+    has fewer rows than one of short ones -- and the buckets are LPT-assigned to the ranks.  With equal-cost buckets and
+    a bucket count that is a multiple of the rank count the assignment is balanced by construction, which plain
+    `bucket_by_length` + `lpt_shard` is not when there are only ~2 buckets per rank.  `max_pad_frac` bounds the padding
+    of the WHOLE workload (padded row-frames vs real frames); if the equal-cost cut exceeds it, more buckets per rank are
+    used.  groups_per_rank=None tries 2, 3 and 4 and keeps the cut with the smallest predicted makespan.
+    Returns (buckets: list of index lists, shards: list (len world_size) of bucket-index lists)."""
+    if groups_per_rank is None:
+        best = None
+        for g_ in (2, 3, 4):
+            b_, s_ = balanced_buckets(n_frames, world_size, g_, max_pad_frac, max_rows)
+            nn = np.asarray(n_frames, dtype=np.int64)
+            span = max(sum(batch_cost_us(nn[b_[i]]) for i in sh) for sh in s_)
+            if best is None or span < best[0]:
+                best = (span, b_, s_)
+        return best[1], best[2]
+    n = np.asarray(n_frames, dtype=np.int64)
+    order = [int(i) for i in np.argsort(-n, kind="stable")]
+
+    def pack(cap_us):
+        """Greedy contiguous packing under a per-bucket cost cap (and the row limit of one decoder scan)."""
+        out, cur = [], []
+        for i in order:
+            cand = cur + [i]
+            if cur and (len(cand) > max_rows or batch_cost_us(n[cand]) > cap_us):
+                out.append(cur)
+                cur = [i]
+            else:
+                cur = cand
+        if cur:
+            out.append(cur)
+        return out
+
+    g = groups_per_rank
+    while True:
+        G = max(1, world_size * g)
+        # smallest cost cap that needs at most G buckets: every bucket then costs about the same (<= cap)
+        lo, hi = float(batch_cost_us(n[order[:1]])), float(batch_cost_us(n[order])) + 1.0
+        for _ in range(40):
+            mid = 0.5 * (lo + hi)
+            if len(pack(mid)) <= G:
+                hi = mid
+            else:
+                lo = mid
+        buckets = pack(hi)
+        padded = sum(len(b) * int(n[b[0]]) for b in buckets)
+        if 1.0 - float(n.sum()) / padded <= max_pad_frac or G >= len(order):
+            break
+        g += 1
+    shards = lpt_shard([int(batch_cost_us(n[b])) for b in buckets], world_size)
+    return buckets, shards
+
+
 def broadcast_blob(blob_np, device, src: int = 0, group=None):
     """Broadcast a float32 blob from rank `src`; returns a torch tensor on `device`
     on every rank.  `blob_np` is only read on rank `src` (other ranks pass the size)."""
