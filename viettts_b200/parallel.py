@@ -47,14 +47,16 @@ def bucket_by_length(n_frames, max_pad_frac: float = 0.08, max_rows: int = 128):
 
 # measured cost model of one ragged batch on a B200 (bench.py `roofline_stages`): the decoder scan is paid per frame of
 # the batch's longest row (sequential, ~20 us per frame for up to 32 rows), everything else per padded row-frame
-SCAN_US_PER_FRAME = 20.0
+SCAN_US_PER_FRAME = 17.0          # + SCAN_US_PER_FRAME_ROW per row of the launch: 17.6 us at 1 row, 18.5 at 8, 21.7 at 32
+SCAN_US_PER_FRAME_ROW = 0.15
 ROW_US_PER_FRAME = 1.9
 
 
 def batch_cost_us(n_frames_of_rows) -> float:
     n = np.asarray(n_frames_of_rows, dtype=np.int64)
-    scans = (len(n) + 31) // 32                       # the decoder scan takes up to 32 rows per launch
-    return float(n.max()) * (SCAN_US_PER_FRAME * scans + ROW_US_PER_FRAME * len(n))
+    rows = len(n)
+    scans = (rows + 31) // 32                         # the decoder scan takes up to 32 rows per launch
+    return float(n.max()) * (SCAN_US_PER_FRAME * scans + SCAN_US_PER_FRAME_ROW * rows + ROW_US_PER_FRAME * rows)
 
 
 def balanced_buckets(n_frames, world_size: int, groups_per_rank=None, max_pad_frac: float = 0.08, max_rows: int = 32):
