@@ -1,6 +1,7 @@
 """CPU restatement of MelFilter (STFT + log-mel).  Test infrastructure only.
 
-PARITY UNPINNED (jax and librosa are absent; the reference has no dsp tests).
+Pinned to the output of the reference's own dsp.py executed on numpy stand-ins for jax / librosa
+(tests/refshim, tests/golden/nat_ref_gta.npz `logmel`, tests/test_reference_goldens.py).
 Follows /root/reference/vietTTS/nat/dsp.py:
 
   rolling_window   dsp.py:11-25

@@ -1,10 +1,10 @@
 """CPU restatement of AcousticModel.inference.  Test infrastructure only.
 
-PARITY UNPINNED: jax / dm-haiku cannot be installed in this environment and the
-reference's tests (tests/test_nat_acoustic.py:9-18) hold no golden vectors, so
-this file restates the reference (file:line below, into /root/reference) using
-the published semantics of the dm-haiku modules it calls.  float64 mode is the
-arbiter for the float32 CUDA path.
+Pinned to golden vectors produced by executing the reference's own source files on numpy stand-ins
+for jax / haiku (tests/refshim, tests/golden/make_nat_golden.py, tests/test_reference_goldens.py): the
+WIRING below is held to the reference at float64; the dm-haiku / jax primitives it relies on are
+restated (jax / dm-haiku cannot be installed here or on the GPU box: profiles/r2_ref_deps_probe_*.json)
+and cross-checked against torch operators.  float64 mode is the arbiter for the float32 CUDA path.
 
   TokenEncoder.__call__      vietTTS/nat/model.py:26-47
   AcousticModel.prenet       vietTTS/nat/model.py:95-100

@@ -1,7 +1,8 @@
 """GPU parity: DurationModel + the text2mel glue (CUDA, through the C ABI) vs the CPU restatement
 (the callers of predict_mel).
 
-Oracle status: UNPINNED (no jax/haiku here; see oracle/__init__.py).  Tolerance: predicted durations are
+Oracle status: pinned to the reference's own source (tests/test_reference_goldens.py; the CUDA path is also compared
+with the reference-produced durations directly in tests/test_gpu_reference_goldens.py).  Tolerance: predicted durations are
 O(0.1 s); |gpu - float64 oracle| <= 2e-5 s in both arithmetic modes (the recurrent part is fp32 in both)."""
 import json
 import pickle

@@ -1,7 +1,7 @@
 """GPU parity: teacher-forced acoustic pass with zoneout (AcousticModel.__call__, model.py:146-169) and the GTA
 forward (gta.py:28-41) vs the CPU restatement.
 
-Oracle status: UNPINNED (see oracle/__init__.py).  Dropout and zoneout masks are explicit inputs shared by both
+Oracle status: pinned to the reference's own source (tests/test_reference_goldens.py, tests/test_gpu_reference_goldens.py).  Dropout and zoneout masks are explicit inputs shared by both
 sides.  Tolerance: mel L-inf <= 1e-3 (log-mel units), the same bar as the autoregressive path."""
 import numpy as np
 import pytest

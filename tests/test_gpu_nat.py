@@ -1,6 +1,7 @@
 """GPU parity: NAT acoustic model (CUDA, through the C ABI) vs the CPU restatement.
 
-The oracle for this stage is UNPINNED (no jax/haiku here; see oracle/__init__.py).
+The oracle for this stage is pinned to the reference's own source (tests/test_reference_goldens.py); the direct
+comparison of the CUDA path with reference-produced vectors is tests/test_gpu_reference_goldens.py.
 Tolerance (fp32, shared dropout masks): mel L-inf <= 1e-3 (log-mel units) after the
 full autoregressive scan; encoder/upsample taps <= 1e-4."""
 import numpy as np

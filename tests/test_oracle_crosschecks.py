@@ -1,6 +1,8 @@
 """Independent cross-checks of the dm-haiku semantics the NAT restatement relies on (oracle/nat_oracle.py).
 
-The NAT oracle is UNPINNED against the real reference (no jax / dm-haiku here).  These tests do the next best
+The NAT oracle's WIRING is pinned by executing the reference's own source on numpy stand-ins for jax / dm-haiku
+(tests/test_reference_goldens.py); the stand-ins and the oracle both restate the third-party primitives, so these
+tests pin the primitives themselves: they do the next best
 thing: every haiku building block it restates is compared with torch's own, independently written implementation
 of the same operator, after mapping haiku's documented parameter layout onto torch's:
   hk.LSTM      gates [i, g, f, o] along the 4H axis, forget-gate bias +1 added at run time, z = [x, h] W + b

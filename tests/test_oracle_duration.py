@@ -1,6 +1,7 @@
 """CPU tests of the DurationModel restatement (oracle/nat_oracle.py; model.py:49-70) and of the blob packing.
 
-PARITY UNPINNED like the rest of the NAT oracle (no jax/haiku here); the checks are the reference's own shape test
+Pinned to the reference's own source since round 2 (tests/test_reference_goldens.py::test_duration_matches_reference_source);
+the earlier structural checks stay: the reference's own shape test
 (tests/test_nat_duration.py:9-15), the dm-haiku / jax function definitions against independent torch
 implementations, and structural properties of the restatement."""
 import numpy as np

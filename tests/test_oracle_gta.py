@@ -1,5 +1,6 @@
 """CPU checks of the teacher-forced / GTA restatement (oracle/nat_oracle.py; model.py:146-169, gta.py:28-41).
-PARITY UNPINNED (no jax/haiku).  Structural pins: (i) the reference's own shape test (tests/test_nat_acoustic.py),
+Since round 2 the restatement is pinned to the reference's own source (tests/test_reference_goldens.py).  The
+structural pins that came first are kept: (i) the reference's own shape test (tests/test_nat_acoustic.py),
 (ii) teacher forcing on the autoregressive path's own output reproduces it when dropout and zoneout are off --
 the two restatements share no decoder code, (iii) zoneout semantics on hand-made masks."""
 import numpy as np
