@@ -268,6 +268,21 @@ __device__ __forceinline__ void dec_fetch(float* xs, int pitch, int koff, const 
   }
 }
 
+// same copy with cp.async (16 B, L2 only): the data goes global -> shared without passing through registers, so a fetch
+// can stay in flight while the CTA computes on operands that have already arrived (decoder_tf_scan_kernel)
+__device__ __forceinline__ void dec_fetch_async(float* xs, int pitch, int koff, const float* p, int n, int stride, int nr) {
+  const int n4 = n >> 2;
+  const int total = nr * n4;
+  for (int e = threadIdx.x; e < total; e += SCAN_THREADS) {
+    const int r = e / n4, i4 = (e - r * n4) * 4;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + (size_t)r * pitch + koff + i4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p + (size_t)r * stride + i4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // acc[8 rows][4 cols] partial sums over this thread's K slice -> butterfly over the 8 slices of the
 // warp (28 shuffles); afterwards the thread holds the warp-level sums of row (lane>>2), cols cg*4..+3.
 __device__ __forceinline__ float4 warp_reduce_rows(float (&acc)[RG][4], int lane) {
@@ -814,11 +829,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_tf_scan_kernel(const 
   const int ngroups = (B + RG - 1) / RG;
   for (int s = 0; s <= N; ++s) {
     // values published in iteration s-1: h0s_{s-1}, h0n_{s-1} (LSTM0 of frame s-1) and h1s_{s-2} (LSTM1 of frame s-2)
+    // three copy groups in flight: LSTM0 of frame s only needs the first one, the operands of LSTM1 (frame s-1) keep
+    // arriving while its product runs
     if (s >= 1) {
-      dec_fetch(xs, TF_PITCH, 0, a.h0s + (size_t)((s - 1) & 1) * B * H, H, H, B);
-      dec_fetch(xs, TF_PITCH, H, a.hout + (size_t)(s - 1) * 2 * H, H, N * 2 * H, B);
+      dec_fetch_async(xs, TF_PITCH, 0, a.h0s + (size_t)((s - 1) & 1) * B * H, H, H, B);
+      dec_fetch_async(xs, TF_PITCH, H, a.hout + (size_t)(s - 1) * 2 * H, H, N * 2 * H, B);
+    } else {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (s >= 2) dec_fetch(xs, TF_PITCH, 2 * H, a.h1s + (size_t)(s & 1) * B * H, H, H, B);
+    if (s >= 2) dec_fetch_async(xs, TF_PITCH, 2 * H, a.h1s + (size_t)(s & 1) * B * H, H, H, B);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_wait<2>();
     __syncthreads();
     if (s < N) {
       // ---- LSTM0 of frame s: z = zc0[s] + h0s_{s-1} . W0[h0 rows] ----
@@ -836,10 +858,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_tf_scan_kernel(const 
         cst[r * UPC + uu] = kc ? c_prev : cc;
       }
     }
+    cp_async_wait<0>();
     if (s >= 1) {
       // ---- LSTM1 of frame s-1: z = zc1[s-1] + h0n_{s-1} . W1[h0 rows] + h1s_{s-2} . W1[h1 rows] ----
       const int t = s - 1;
-      __syncthreads();    // zs is reused
+      __syncthreads();    // zs is reused; every thread's copies of the LSTM1 operands have landed
       dec_matmul2<SLH, SLH, TF_PITCH>(xs + H, w1h0, xs + 2 * H, w1h1, ngroups, part, zs, nullptr);
       if (tid < B * UPC) {
         const int r = tid / UPC, uu = tid % UPC, u = c * UPC + uu;
