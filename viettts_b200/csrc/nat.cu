@@ -236,7 +236,8 @@ struct DecScanArgs {
   long long* dbg;        // optional per-CTA phase timers [grid][16]
 };
 
-constexpr int DEC_XR = 32;                 // batch rows per launch
+constexpr int DEC_XR = 32;                 // batch rows per staging group (smem holds the state of one group)
+constexpr int DEC_NG = 4;                  // row groups per launch: up to 128 rows share the three grid barriers of a frame
 constexpr int DEC_KPAD = vc::PRENET + 2 * vc::DEC_H + 4;   // 1284: [p2 | h0 | h1] + pad
 constexpr int DEC_LSTM = 128, DEC_PRE = 16;
 constexpr int DEC_CTAS = DEC_LSTM + DEC_PRE;   // 144
@@ -591,12 +592,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
 
   if (c < DEC_LSTM) {
     // =============================== LSTM role ===============================
-    float* xs = sm;                                   // [DEC_XR][DEC_KPAD] = [p2 | h0 | h1]
+    float* xs = sm;                                   // [DEC_XR][DEC_KPAD] = [p2 | h0 | h1] of ONE row group at a time
     float* part = xs + DEC_XR * DEC_KPAD;             // [8][DEC_XR][16]
     float* zs = part + 8 * DEC_XR * NCOL;             // [DEC_XR][16]
-    float* zp0 = zs + DEC_XR * NCOL;                  // [DEC_XR][16] pre-accumulated h0_{t-1} . W0[h0 rows]
-    float* zp1 = zp0 + DEC_XR * NCOL;                 // [DEC_XR][16] pre-accumulated h1_{t-1} . W1[h1 rows] (+ p2 . W1[p2 rows])
-    float* cst = zp1 + DEC_XR * NCOL;                 // [2][DEC_XR][UPC]
+    float* zp0 = zs + DEC_XR * NCOL;                  // [DEC_NG][DEC_XR][16] pre-accumulated h0_{t-1} . W0[h0 rows]
+    float* zp1 = zp0 + DEC_NG * DEC_XR * NCOL;        // [DEC_NG][DEC_XR][16] pre-accumulated h1_{t-1} . W1[h1 rows]
+    float* cst = zp1 + DEC_NG * DEC_XR * NCOL;        // [DEC_NG][2][DEC_XR][UPC]
     const int ks = tid >> 2, cgp = tid & 3;
     constexpr int SLP = vc::PRENET / NSLICE, SLH = H / NSLICE;   // 4, 8
     // register-resident weight slices, split by input segment so that each segment's product can be
@@ -618,18 +619,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
         ld(w1h1[i], g1, vc::PRENET + H + ks * SLH + i);
       }
     }
-    for (int e = tid; e < 2 * DEC_XR * UPC; e += SCAN_THREADS) cst[e] = 0.f;
-    for (int e = tid; e < 2 * DEC_XR * NCOL; e += SCAN_THREADS) zp0[e] = 0.f;   // zp0 and zp1 are adjacent
+    for (int e = tid; e < DEC_NG * 2 * DEC_XR * UPC; e += SCAN_THREADS) cst[e] = 0.f;
+    for (int e = tid; e < DEC_NG * 2 * DEC_XR * NCOL; e += SCAN_THREADS) zp0[e] = 0.f;   // zp0 and zp1 are adjacent
     for (int e = tid; e < DEC_XR * DEC_KPAD; e += SCAN_THREADS) xs[e] = 0.f;    // rows >= B and the t=0 state are zero
     __syncthreads();
-    const int ngroups = (B + RG - 1) / RG;
+    // Rows are processed in groups of DEC_XR (the staging buffer holds one group); all groups of a launch share the
+    // three grid barriers of a frame.  With one group, h0_{t-1} and p2 stay resident in xs between the phases.
+    const int NG = (B + DEC_XR - 1) / DEC_XR;
     for (int t = 0; t < N; ++t) {
       // ---- EA window (prenet CTAs are busy): products of the state that is already final ----
       if (t > 0) {
-        // h0_{t-1} is still resident in xs (fetched as h0_t in phase D of the previous frame); only h1_{t-1} is new
-        dec_fetch(xs, DEC_KPAD, vc::PRENET + H, a.h1 + (size_t)((t - 1) & 1) * B * H, H, H, B);
-        dec_matmul<SLH>(xs + vc::PRENET, w0h, ngroups, part, zp0, nullptr);     // its barriers also order the h1 fetch
-        dec_matmul<SLH>(xs + vc::PRENET + H, w1h1, ngroups, part, zp1, nullptr);
+        for (int rg = 0; rg < NG; ++rg) {
+          const int r0 = rg * DEC_XR, nb = min(DEC_XR, B - r0), ngroups = (nb + RG - 1) / RG;
+          if (NG > 1) dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + ((size_t)((t - 1) & 1) * B + r0) * H, H, H, nb);
+          dec_fetch(xs, DEC_KPAD, vc::PRENET + H, a.h1 + ((size_t)((t - 1) & 1) * B + r0) * H, H, H, nb);
+          if (NG > 1) __syncthreads();
+          dec_matmul<SLH>(xs + vc::PRENET, w0h, ngroups, part, zp0 + rg * DEC_XR * NCOL, nullptr);     // its barriers also order the h1 fetch
+          dec_matmul<SLH>(xs + vc::PRENET + H, w1h1, ngroups, part, zp1 + rg * DEC_XR * NCOL, nullptr);
+        }
       }
       DEC_MARK(0)
       DEC_MARK(1)
@@ -637,35 +644,45 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       grid.sync();   // p2(t) is ready (the prenet CTAs order their two layers among themselves, see prenet_barrier)
       DEC_MARK(3)
       // ---- phase C: LSTM0 = zc0[t] + p2 . W0[p2 rows] + (h0_{t-1} part) ----
-      dec_fetch(xs, DEC_KPAD, 0, a.p2, vc::PRENET, vc::PRENET, B);
-      __syncthreads();
-      dec_matmul<SLP>(xs, w0p, ngroups, part, zs, zp0);
-      if (tid < B * UPC) {
-        const int r = tid / UPC, uu = tid % UPC;
-        const float* zc = a.zc0 + ((size_t)r * N + t) * (4 * H) + c * UPC + uu;
-        float cc = cst[r * UPC + uu];
-        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
-        cst[r * UPC + uu] = cc;
-        a.h0[((size_t)(t & 1) * B + r) * H + c * UPC + uu] = h;
-        a.hout[((size_t)r * N + t) * 2 * H + c * UPC + uu] = h;
+      for (int rg = 0; rg < NG; ++rg) {
+        const int r0 = rg * DEC_XR, nb = min(DEC_XR, B - r0), ngroups = (nb + RG - 1) / RG;
+        dec_fetch(xs, DEC_KPAD, 0, a.p2 + (size_t)r0 * vc::PRENET, vc::PRENET, vc::PRENET, nb);
+        __syncthreads();
+        dec_matmul<SLP>(xs, w0p, ngroups, part, zs, zp0 + rg * DEC_XR * NCOL);
+        if (tid < nb * UPC) {
+          const int r = tid / UPC, uu = tid % UPC, rb = r0 + r;
+          const float* zc = a.zc0 + ((size_t)rb * N + t) * (4 * H) + c * UPC + uu;
+          float* cs = cst + (size_t)rg * 2 * DEC_XR * UPC;
+          float cc = cs[r * UPC + uu];
+          const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
+          cs[r * UPC + uu] = cc;
+          a.h0[((size_t)(t & 1) * B + rb) * H + c * UPC + uu] = h;
+          a.hout[((size_t)rb * N + t) * 2 * H + c * UPC + uu] = h;
+        }
+        if (NG > 1) __syncthreads();    // zs and xs are reused by the next group
       }
       DEC_MARK(4)
       grid.sync();
       DEC_MARK(5)
       // ---- phase D: LSTM1 = zc1[t] + p2 . W1[p2 rows] + h0_t . W1[h0 rows] + (h1_{t-1} part) ----
-      dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + (size_t)(t & 1) * B * H, H, H, B);
-      __syncthreads();
-      dec_matmul2<SLP, SLH>(xs, w1p, xs + vc::PRENET, w1h0, ngroups, part, zs, zp1);
-      if (tid < B * UPC) {
-        const int r = tid / UPC, uu = tid % UPC;
-        const float* zc = a.zc1 + ((size_t)r * N + t) * (4 * H) + c * UPC + uu;
-        float cc = cst[(DEC_XR + r) * UPC + uu];
-        const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
-        cst[(DEC_XR + r) * UPC + uu] = cc;
-        a.h1[((size_t)(t & 1) * B + r) * H + c * UPC + uu] = h;
-        a.hout[((size_t)r * N + t) * 2 * H + H + c * UPC + uu] = h;
+      for (int rg = 0; rg < NG; ++rg) {
+        const int r0 = rg * DEC_XR, nb = min(DEC_XR, B - r0), ngroups = (nb + RG - 1) / RG;
+        if (NG > 1) dec_fetch(xs, DEC_KPAD, 0, a.p2 + (size_t)r0 * vc::PRENET, vc::PRENET, vc::PRENET, nb);
+        dec_fetch(xs, DEC_KPAD, vc::PRENET, a.h0 + ((size_t)(t & 1) * B + r0) * H, H, H, nb);
+        __syncthreads();
+        dec_matmul2<SLP, SLH>(xs, w1p, xs + vc::PRENET, w1h0, ngroups, part, zs, zp1 + rg * DEC_XR * NCOL);
+        if (tid < nb * UPC) {
+          const int r = tid / UPC, uu = tid % UPC, rb = r0 + r;
+          const float* zc = a.zc1 + ((size_t)rb * N + t) * (4 * H) + c * UPC + uu;
+          float* cs = cst + (size_t)rg * 2 * DEC_XR * UPC;
+          float cc = cs[(DEC_XR + r) * UPC + uu];
+          const float h = lstm_cell(zs, r, uu, __ldg(zc), __ldg(zc + H), __ldg(zc + 2 * H), __ldg(zc + 3 * H), cc);
+          cs[(DEC_XR + r) * UPC + uu] = cc;
+          a.h1[((size_t)(t & 1) * B + rb) * H + c * UPC + uu] = h;
+          a.hout[((size_t)rb * N + t) * 2 * H + H + c * UPC + uu] = h;
+        }
+        __syncthreads();
       }
-      __syncthreads();
       DEC_MARK(6)
       grid.sync();
       DEC_MARK(7)
@@ -681,28 +698,33 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
     float* w2s = wcs + 2 * WCB;                        // [2][W2B]
     float* part = w2s + 2 * W2B;                       // [8][32][8]
     float* outv = part + 8 * 256;                      // [256]
-    float* pp1 = outv + 256;                           // [2][256] h0 half of p1's pre-activation, computed one phase early
+    float* pp1 = outv + 256;                           // [DEC_NG][2][256] h0 half of p1's pre-activation, computed one phase early
     for (int hf = 0; hf < 2; ++hf) {
       pre_load_w8(wcs + (size_t)hf * WCB, a.wc + (size_t)q * 2 * H * 16, 2 * H, 8, 16, hf * 8);
       pre_load_w8(w2s + (size_t)hf * W2B, a.wp2 + (size_t)q * vc::PRENET * 16, vc::PRENET, 4, 16, hf * 8);
     }
     for (int e = tid; e < 32 * XP; e += SCAN_THREADS) xs[e] = 0.f;
-    for (int e = tid; e < 512; e += SCAN_THREADS) pp1[e] = 0.f;
+    for (int e = tid; e < DEC_NG * 512; e += SCAN_THREADS) pp1[e] = 0.f;
     __syncthreads();
     const int orow = tid >> 3, ocol = tid & 7;         // output handled by this thread after a pre_gemm8 pass
     constexpr int H1OFF = (H + H / 8) * 8;             // first padded row of the h1 half inside a WCB block
+    const int NG = (B + DEC_XR - 1) / DEC_XR;
     for (int t = 0; t < N; ++t) {
       // ---- phase EA: p1(t) = drop(relu(pp1 + h1_{t-1} . Wc[512:1024] + bc)) ----
       if (t > 0) {
-        dec_fetch(xs, XP, 0, a.h1 + (size_t)((t - 1) & 1) * B * H, H, H, B);
-        __syncthreads();
+        for (int rg = 0; rg < NG; ++rg) {
+          const int r0 = rg * DEC_XR, nb = min(DEC_XR, B - r0);
+          if (NG > 1) __syncthreads();
+          dec_fetch(xs, XP, 0, a.h1 + ((size_t)((t - 1) & 1) * B + r0) * H, H, H, nb);
+          __syncthreads();
 #pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
-          pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB + H1OFF, part, outv);
-          if (orow < B) {
-            const int u = q * 16 + hf * 8 + ocol;
-            const float v = fmaxf(outv[tid] + pp1[hf * 256 + tid] + __ldg(a.bc + u), 0.f);
-            a.p1[(size_t)orow * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + orow, t, N, 0, u);
+          for (int hf = 0; hf < 2; ++hf) {
+            pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB + H1OFF, part, outv);
+            if (orow < nb) {
+              const int u = q * 16 + hf * 8 + ocol;
+              const float v = fmaxf(outv[tid] + pp1[rg * 512 + hf * 256 + tid] + __ldg(a.bc + u), 0.f);
+              a.p1[(size_t)(r0 + orow) * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + r0 + orow, t, N, 0, u);
+            }
           }
         }
       } else {
@@ -712,15 +734,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       prenet_barrier(a.pre_bar, (unsigned)DEC_PRE * (unsigned)(t + 1), a.err);   // every column block of p1(t) is in L2
       DEC_MARK(1)
       // ---- phase B: p2(t) = drop(relu(p1 . W2)) ----
-      dec_fetch(xs, XP, 0, a.p1, vc::PRENET, vc::PRENET, B);
-      __syncthreads();
+      for (int rg = 0; rg < NG; ++rg) {
+        const int r0 = rg * DEC_XR, nb = min(DEC_XR, B - r0);
+        if (NG > 1) __syncthreads();
+        dec_fetch(xs, XP, 0, a.p1 + (size_t)r0 * vc::PRENET, vc::PRENET, vc::PRENET, nb);
+        __syncthreads();
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
-        pre_gemm8<4>(xs, XP, w2s + (size_t)hf * W2B, part, outv);
-        if (orow < B) {
-          const int u = q * 16 + hf * 8 + ocol;
-          const float v = fmaxf(outv[tid], 0.f);
-          a.p2[(size_t)orow * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + orow, t, N, 1, u);
+          pre_gemm8<4>(xs, XP, w2s + (size_t)hf * W2B, part, outv);
+          if (orow < nb) {
+            const int u = q * 16 + hf * 8 + ocol;
+            const float v = fmaxf(outv[tid], 0.f);
+            a.p2[(size_t)(r0 + orow) * vc::PRENET + u] = v * keep_scale(a.mode, a.keep, a.seed, a.row_base + r0 + orow, t, N, 1, u);
+          }
         }
       }
       DEC_MARK(2)
@@ -729,13 +755,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) decoder_scan_kernel(const Dec
       grid.sync();
       DEC_MARK(5)
       // ---- D window: h0_t is final -> its half of p1(t+1)'s pre-activation ----
-      __syncthreads();
-      dec_fetch(xs, XP, 0, a.h0 + (size_t)(t & 1) * B * H, H, H, B);
-      __syncthreads();
+      for (int rg = 0; rg < NG; ++rg) {
+        const int r0 = rg * DEC_XR, nb = min(DEC_XR, B - r0);
+        __syncthreads();
+        dec_fetch(xs, XP, 0, a.h0 + ((size_t)(t & 1) * B + r0) * H, H, H, nb);
+        __syncthreads();
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
-        pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB, part, outv);
-        pp1[hf * 256 + tid] = outv[tid];
+          pre_gemm8<8>(xs, XP, wcs + (size_t)hf * WCB, part, outv);
+          pp1[rg * 512 + hf * 256 + tid] = outv[tid];
+        }
       }
       __syncthreads();
       DEC_MARK(6)
@@ -900,8 +929,8 @@ constexpr size_t enc_scan_smem() {
   return ((size_t)32 * (vc::ENC_D + 4) + 8 * DEC_XR * NCOL + DEC_XR * NCOL + MAX_ROWS * UPC) * 4;
 }
 constexpr size_t dec_scan_smem() {
-  constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + 3 * DEC_XR * NCOL + 2 * DEC_XR * UPC;
-  constexpr size_t pre = (size_t)32 * (vc::DEC_H + 4) + 2 * (2 * vc::DEC_H + 2 * vc::DEC_H / 8) * 8 + 2 * (vc::PRENET + NSLICE) * 8 + 8 * 256 + 256 + 512;
+  constexpr size_t lstm = (size_t)DEC_XR * DEC_KPAD + 8 * DEC_XR * NCOL + DEC_XR * NCOL + DEC_NG * (2 * DEC_XR * NCOL + 2 * DEC_XR * UPC);
+  constexpr size_t pre = (size_t)32 * (vc::DEC_H + 4) + 2 * (2 * vc::DEC_H + 2 * vc::DEC_H / 8) * 8 + 2 * (vc::PRENET + NSLICE) * 8 + 8 * 256 + 256 + DEC_NG * 512;
   return (lstm > pre ? lstm : pre) * 4;
 }
 
@@ -1102,8 +1131,8 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   float* p1 = ar.take<float>((size_t)B * 256);
   float* p2 = ar.take<float>((size_t)B * 256);
   float* hout = ar.take<float>(BN * 1024);
-  float* h0 = ar.take<float>((size_t)2 * DEC_XR * 512);
-  float* h1 = ar.take<float>((size_t)2 * DEC_XR * 512);
+  float* h0 = ar.take<float>((size_t)2 * MAX_ROWS * 512);
+  float* h1 = ar.take<float>((size_t)2 * MAX_ROWS * 512);
   unsigned int* pre_bar = ar.take<unsigned int>(64);
   if (measure) {
     *ws_need = ar.off + 256;
@@ -1155,9 +1184,9 @@ int vtts_acoustic_run(vtts_ctx* ctx, const int32_t* tokens, const int32_t* lengt
   int rc = vtts_conv_dispatch(ctx, Lc, &ctx->ac_wpk_t[WP_DECH], st);
   if (rc) return rc;
   ctx->sub_mark(3, st);
-  // ---- autoregressive scan: launches of up to 32 rows (rows are independent) ----
-  for (int b0 = 0; b0 < B; b0 += DEC_XR) {
-    const int nb = B - b0 < DEC_XR ? B - b0 : DEC_XR;
+  // ---- autoregressive scan: ONE launch for up to DEC_NG * 32 rows (row groups share the grid barriers of a frame) ----
+  for (int b0 = 0; b0 < B; b0 += DEC_NG * DEC_XR) {
+    const int nb = B - b0 < DEC_NG * DEC_XR ? B - b0 : DEC_NG * DEC_XR;
     DecScanArgs da;
     memset(&da, 0, sizeof(da));
     da.zc0 = zc0 + (size_t)b0 * N * 2048; da.zc1 = zc1 + (size_t)b0 * N * 2048;
