@@ -264,6 +264,7 @@ int vtts_create(int device, vtts_ctx** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->hbm_bytes = prop.totalGlobalMem;
+  if (const char* v = getenv("VTTS_TC_VARIANT")) ctx->tc_variant = atoi(v);   // tuning aid (same values as vtts_debug_tc_stats bits 4..7)
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_vtts_create_error = std::string("vtts_create: ") + cudaGetErrorString(e);
     delete ctx;

@@ -23,6 +23,17 @@
 //   warps 6-13 activation converters: fp32 global -> [mean3] -> leaky_relu -> hi/lo bf16 -> smem
 // A "super tile" is MT = min(4, 512/N) M-tiles (128*MT rows) that share every weight stage, so a
 // weight block fetched from L2 feeds MT MMAs.
+//
+// N >= 128 runs in the CTA-PAIR form by default (template parameter PAIR, tc_variant 3): the grid is 74 clusters of two
+// CTAs, a tile is 2 x 128*MT rows, and rank 0 issues `tcgen05.mma.cta_group::2` (M = 256) for both SMs: each CTA
+// converts its own rows and fetches only ITS HALF of every weight block, so the shared-memory operand bytes per MMA drop
+// from 8 KB to 6 KB (N = 128) and the instruction runs at the math rate (66 instead of 97 clk, scripts/umma_probe3.cu).
+//   * barriers the issuer waits on (a_full, w_full, tmem_empty) live in rank 0 and count the arrivals of both CTAs;
+//     rank 1's threads arrive through `mapa` + `mbarrier.arrive.shared::cluster` (release at CTA scope -- a cluster-
+//     scope release costs ~1000 clk per arrive), rank 1's otherwise idle warp 4 forwards its weight-stage completions;
+//   * `tcgen05.commit ... multicast::cluster` frees the stages / publishes the accumulators in both CTAs at once;
+//   * weight stages are grouped four taps per barrier so that the issuing warp spends one wait + one elected region
+//     per 24 MMAs (its loop otherwise costs about as much as the MMAs of one tap take at the math rate).
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -34,7 +45,7 @@ namespace {
 
 using namespace tcx;
 
-constexpr int NA = 4;               // activation stages
+constexpr int NA_DEFAULT = 4;       // activation stages (single-CTA form)
 constexpr int NW_MAX = 8;            // weight stages: 6 x 16 KB for N = 256, 8 smaller ones otherwise (covers the L2 latency)
 constexpr int COLL = 1;          // A-operand collector reuse between the a_hi x W_hi and a_hi x W_lo MMAs
 constexpr int NTHREADS = 576;     // 4 epilogue + MMA + weight producer + 8 converter + 4 more epilogue warps
@@ -46,17 +57,32 @@ constexpr int GRP_THREADS = NCONV / NGRP;
 // MT  = M-tiles (128 rows) per super tile, NPH = output phases accumulated per tile (ConvTranspose), the
 // accumulator set of a tile is NPH*MT*N TMEM columns; two sets (epilogue overlaps the next tile's MMAs) when
 // they fit in the 512 columns.
-template <int N, int MT_, int NPH_, int STK_ = 0>
+// PAIR = 1: two CTAs of a cluster work as one (tcgen05 cta_group::2, M = 256): each CTA converts the activations of its
+// own 128*MT rows and fetches HALF of every weight block (the output columns [N/2 r, N/2 r + N/2) of rank r), the MMAs
+// are issued by rank 0 for both SMs -- the shared-memory operand traffic per FLOP drops by the weight half, which is
+// what bounds the single-CTA form (scripts/umma_probe3.cu: 66 instead of 97 clk per N=128 MMA).
+template <int N, int MT_, int NPH_, int STK_ = 0, int PAIR_ = 0>
 struct TcCfg {
   static constexpr int MT = MT_;
   static constexpr int NPH = NPH_;
   static constexpr int STK = STK_;            // 1: A_hi x [W_hi | W_lo] as ONE MMA of width 2N (main | aux accumulator columns)
+  static constexpr int PAIR = PAIR_;
+  static constexpr int CPP = PAIR ? 2 : 1;    // CTAs per tile
+  static constexpr int NB = N / CPP;          // weight rows (output columns) held by one CTA
+  static_assert(!(PAIR && STK), "the pair form keeps three MMAs per product");
   static constexpr int DW = STK ? 2 * N : N;  // accumulator columns per (phase, M tile)
-  static constexpr int NW = N == 256 ? 6 : ((N == 128 && MT_ == 4) ? 4 : NW_MAX);
+  // weight ring: NW groups of G taps behind ONE barrier pair each.  The pair form's MMAs run at the math rate (6 MMAs of
+  // a tap = 384 clk), which is about what one wait + one elected issue region + one commit cost the issuing warp, so
+  // it handles G = 4 taps per region; the single-CTA form (>= 510 clk of MMAs per tap) keeps G = 1.
+  static constexpr int G = PAIR_ ? 4 : 1;
+  static constexpr int NW = PAIR_ ? (N == 256 ? 3 : 4) : (N == 256 ? 6 : ((N == 128 && MT_ == 4) ? 4 : NW_MAX));
+  static constexpr int NA = NA_DEFAULT;   // (6 stages in the pair form measured slower: the converters then crowd out the epilogue's loads)
   static constexpr int R = 128 * MT;          // output rows per super tile
   static constexpr int RA = R + 64;           // allocated activation rows per stage (halo <= 50)
   static constexpr int A_STAGE = RA * 64;     // bytes: 2 planes x 2 k-halves x RA rows x 16 B
-  static constexpr int W_STAGE = N * 64;      // bytes: 2 planes x 2 k-halves x N rows x 16 B
+  static constexpr int W_STAGE = NB * 64;     // bytes: 2 planes x 2 k-halves x NB rows x 16 B
+  static constexpr int W_BLOCK = N * 64;      // bytes of one packed (chunk, tap) block in global memory
+  static constexpr int W_GROUP = G * W_STAGE; // bytes of one ring slot
   static constexpr int ACC_COLS = NPH * MT * DW;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
@@ -65,21 +91,22 @@ struct TcCfg {
   static constexpr int NBAR = 2 * NA + 2 * NW + 2 * NACC;
   static constexpr int EPI_PITCH = 144;                      // bytes per staged row: 32 floats + 16 B pad (conflict-free)
   static constexpr int EPI_STAGE = 8 * 32 * EPI_PITCH;       // one 32-row slab per epilogue warp
-  static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_STAGE + EPI_STAGE + NBAR * 8 + 16 + 1024;
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_GROUP + EPI_STAGE + NBAR * 8 + 16 + 1024;
 };
 
 // EPI = 0: bias (+ residual) only -- the HiFiGAN generator's hot path.  EPI = 1: bias, eval BatchNorm,
 // tanh / relu, residual, partial N tile (acoustic model convs and GEMMs).
-template <int N, int EPI, int MT_, int NPH_, int STK_>
+template <int N, int EPI, int MT_, int NPH_, int STK_, int PAIR_>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_constant__ TcLaunch L) {
-  using Cfg = TcCfg<N, MT_, NPH_, STK_>;
+  using Cfg = TcCfg<N, MT_, NPH_, STK_, PAIR_>;
   constexpr int MT = Cfg::MT, R = Cfg::R, RA = Cfg::RA, NPH = Cfg::NPH, STK = Cfg::STK, DW = Cfg::DW, NW = Cfg::NW;
+  constexpr int PAIR = Cfg::PAIR, CPP = Cfg::CPP, NB = Cfg::NB, G = Cfg::G, NA = Cfg::NA;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_st = smem;
   constexpr int NACC = Cfg::NACC;
   uint8_t* w_st = smem + NA * Cfg::A_STAGE;
-  uint8_t* epi_st = w_st + NW * Cfg::W_STAGE;
+  uint8_t* epi_st = w_st + NW * Cfg::W_GROUP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_st + Cfg::EPI_STAGE);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + NA;
@@ -92,19 +119,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index broadcast from lane 0: provably warp-uniform, so role code can live on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  // pair form: the barriers the issuer (rank 0) waits on collect the arrivals of BOTH CTAs (the peer arrives through
+  // the cluster address space); a_empty / w_empty / tmem_full are signalled in both CTAs by the multicast commit
+  const uint32_t prank = PAIR ? cluster_rank() : 0u;
 
   if (warp == 5 && lane == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], GRP_THREADS); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NEPI); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], CPP * GRP_THREADS); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], (PAIR && prank == 0) ? 2 : 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CPP * NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // the peer's barriers exist before anything is signalled across
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -116,18 +152,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
 
   // every role walks the same tile sequence
 #define TILE_LOOP_BEGIN                                                        \
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {              \
+  for (int tile = blockIdx.x / CPP; tile < ntiles; tile += gridDim.x / CPP) {  \
     const int pi = L.problem_major ? tile / tiles_per_prob : tile % L.nprob;    \
     const int rest = L.problem_major ? tile - pi * tiles_per_prob : tile / L.nprob; \
     const int tt = rest % tiles_per_row;                                       \
     const int b = rest / tiles_per_row;                                        \
-    const int tau0 = tt * R;                                                   \
+    const int tau0 = (tt * CPP + (int)prank) * R;                              \
     int valid = L.T_rows;                                                      \
     if (L.len) {                                                               \
       const int v = L.len[b] * L.len_mul;                                      \
       valid = v < valid ? v : valid;                                           \
     }                                                                          \
-    if (tau0 >= valid) continue;                                               \
+    if (tt * CPP * R >= valid) continue;     /* the same decision in both CTAs of a pair */ \
     const TcProb& P = L.p[pi];                                                 \
     int sh_min = P.in_off_ph[0], sh_max = P.in_off_ph[0];                      \
     _Pragma("unroll") for (int ph_ = 1; ph_ < NPH; ++ph_) {                    \
@@ -136,48 +172,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     }
 #define TILE_LOOP_END }
 
-  if (warp == 4) {
+  if (warp == 4 && PAIR && prank != 0) {
+    // ============================ pair form, rank 1: weight-stage forwarder ============================
+    // this CTA's half of a weight block lands on its own w_full (bulk-copy complete_tx); tell the issuer in rank 0
+    uint32_t sw = 0, pw = 0;
+    long long w_w = 0;
+    TILE_LOOP_BEGIN
+      (void)b; (void)tau0; (void)sh_max;
+      const int k = P.k;
+      const int nst = nch * NPH * ((k + G - 1) / G);
+      for (int s = 0; s < nst; ++s) {
+        mbar_wait_t(&w_full[sw], pw, L.err, 3, w_w);
+        // (release at CTA scope: the data was written by the bulk copy, not by this thread.  A release at CLUSTER scope
+        //  costs ~1000 clk per arrive and made this hop the bottleneck of the whole kernel: VTTS_PAIR_EXP=4 shows it)
+        if (elect_one()) { if (L.exp & 4) mbar_arrive_rank<1>(&w_full[sw], 0); else mbar_arrive_rank<0>(&w_full[sw], 0); }
+        __syncwarp();
+        if (++sw == NW) { sw = 0; pw ^= 1; }
+      }
+    TILE_LOOP_END
+    if (L.dbg && lane == 0) L.dbg[(size_t)blockIdx.x * 16 + 3] = w_w;
+  } else if (warp == 4) {
     // ============================ MMA issuer ============================
     // The whole warp walks the pipeline (uniform control flow, operands in uniform registers); only the
     // tcgen05.mma / tcgen05.commit instructions themselves are predicated on one elected lane.
     {
-      constexpr uint32_t idesc = make_idesc(N);
+      constexpr uint32_t idesc = PAIR ? make_idesc2(N) : make_idesc(N);
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0, acc = 0, tph = 0;
       long long w_tmem = 0, w_a = 0, w_w = 0;
       const long long t_begin = clock64();
       const uint32_t a_st_u32 = smem_u32(a_st), w_st_u32 = smem_u32(w_st);
       // descriptor templates: start address added per use (row stride 16 B == 1 descriptor address unit)
       const uint64_t a_tmpl = make_desc(0, RA * 16, 128);
-      const uint64_t b_tmpl = make_desc(0, 2 * N * 16, 128);     // k-half blocks are 2N rows apart ([hi rows | lo rows])
+      const uint64_t b_tmpl = make_desc(0, 2 * NB * 16, 128);    // k-half blocks are 2 NB rows apart ([hi rows | lo rows])
       constexpr uint32_t idesc2 = make_idesc(2 * N <= 256 ? 2 * N : N);
       TILE_LOOP_BEGIN
         (void)b; (void)tau0;
         const int k = P.k, dil = P.dil;
-        mbar_wait_t(&tmem_empty[acc], tph ^ 1, L.err, 1, w_tmem);
+        if constexpr (PAIR) { if (L.exp & 1) mbar_wait_tc<1>(&tmem_empty[acc], tph ^ 1, L.err, 1, w_tmem); else mbar_wait_tc(&tmem_empty[acc], tph ^ 1, L.err, 1, w_tmem); }
+        else mbar_wait_t(&tmem_empty[acc], tph ^ 1, L.err, 1, w_tmem);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * Cfg::ACC_COLS;
         for (int c = 0; c < nch; ++c) {
-          mbar_wait_t(&a_full[sa], pa, L.err, 2, w_a);
+          if constexpr (PAIR) { if (L.exp & 1) mbar_wait_tc<1>(&a_full[sa], pa, L.err, 2, w_a); else mbar_wait_tc(&a_full[sa], pa, L.err, 2, w_a); }
+          else mbar_wait_t(&a_full[sa], pa, L.err, 2, w_a);
           tc_fence_after();
           const uint32_t a_base16 = (a_st_u32 + sa * Cfg::A_STAGE) >> 4;
 #pragma unroll 1
           for (int ph = 0; ph < NPH; ++ph) {
             const int shift = P.in_off_ph[ph] - sh_min;
-            for (int j = 0; j < k; ++j) {
-              mbar_wait_t(&w_full[sw], pw, L.err, 3, w_w);
+            for (int j0 = 0; j0 < k; j0 += G) {
+              if constexpr (PAIR) { if (L.exp & 1) mbar_wait_tc<1>(&w_full[sw], pw, L.err, 3, w_w); else mbar_wait_tc(&w_full[sw], pw, L.err, 3, w_w); }
+              else mbar_wait_t(&w_full[sw], pw, L.err, 3, w_w);
               tc_fence_after();
-              const uint32_t w_base16 = (w_st_u32 + sw * Cfg::W_STAGE) >> 4;
-              const uint64_t b_hi = b_tmpl | (uint64_t)w_base16;
-              const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + N);
-              const uint32_t first = (c | j) != 0 ? 1u : 0u;
+              const int gn = (G == 1 || k - j0 >= G) ? G : k - j0;     // taps in this group
               if (elect_one()) {
+               for (int jj = 0; jj < gn; ++jj) {
+                const int j = j0 + jj;
+                const uint32_t w_base16 = (w_st_u32 + sw * Cfg::W_GROUP + jj * Cfg::W_STAGE) >> 4;
+                const uint64_t b_hi = b_tmpl | (uint64_t)w_base16;
+                const uint64_t b_lo = b_tmpl | (uint64_t)(w_base16 + NB);
+                const uint32_t first = (c | j) != 0 ? 1u : 0u;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                   const uint32_t row = a_base16 + mt * 128 + shift + j * dil;
                   const uint64_t a_hi = a_tmpl | (uint64_t)row;
                   const uint64_t a_lo = a_tmpl | (uint64_t)(row + 2 * RA);
                   const uint32_t d = d0 + (ph * MT + mt) * DW;
-                  if constexpr (STK) {
+                  if constexpr (PAIR) {
+                    umma2<1>(d, a_hi, b_hi, idesc, first);
+                    umma2<2>(d, a_hi, b_lo, idesc, 1u);
+                    umma2<0>(d, a_lo, b_hi, idesc, 1u);
+                  } else if constexpr (STK) {
                     umma(d, a_hi, b_hi, idesc2, first);     // [main | aux] (+)= A_hi . [W_hi | W_lo]
                     umma(d, a_lo, b_hi, idesc, 1u);         // main += A_lo . W_hi
                   } else {
@@ -186,15 +251,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
                     umma(d, a_lo, b_hi, idesc, 1u);
                   }
                 }
-                umma_commit(&w_empty[sw]);
+               }
+                if constexpr (PAIR) umma_commit2(&w_empty[sw]); else umma_commit(&w_empty[sw]);
               }
               if (++sw == NW) { sw = 0; pw ^= 1; }
             }
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);
+          if (elect_one()) { if constexpr (PAIR) umma_commit2(&a_empty[sa]); else umma_commit(&a_empty[sa]); }
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
+        if (elect_one()) { if constexpr (PAIR) umma_commit2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
         if (++acc == NACC) { acc = 0; tph ^= 1; }
       TILE_LOOP_END
       if (L.dbg && lane == 0) {
@@ -205,24 +271,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
     __syncwarp();
   } else if (warp == 5) {
     // ============================ weight producer ============================
-    if (lane == 0) {
+    if (PAIR || lane == 0) {
+      // (pair form: the whole warp walks the loop and one elected lane issues, so the four bulk copies of a stage
+      //  come from uniform code)
       uint32_t sw = 0, pw = 0;
       long long w_e = 0;
       TILE_LOOP_BEGIN
-        (void)b; (void)tau0;
         const int k = P.k;
+        (void)b; (void)tau0;
         for (int c = 0; c < nch; ++c)
           for (int ph = 0; ph < NPH; ++ph) {
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk_ph[ph]) + (size_t)c * k * Cfg::W_STAGE;
-            for (int j = 0; j < k; ++j) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk_ph[ph]) + (size_t)c * k * Cfg::W_BLOCK;
+            for (int j = 0; j < k; j += G) {
               mbar_wait_t(&w_empty[sw], pw ^ 1, L.err, 4, w_e);
-              mbar_expect_tx(&w_full[sw], Cfg::W_STAGE);
-              bulk_g2s(w_st + sw * Cfg::W_STAGE, wsrc + (size_t)j * Cfg::W_STAGE, Cfg::W_STAGE, &w_full[sw]);
+              if constexpr (PAIR) {
+                // the packed block is [k-half][plane][N rows][16 B]: this CTA's NB rows of each of the four sub-blocks
+                const int gn = k - j >= G ? G : k - j;
+                if (elect_one()) {
+                  mbar_expect_tx(&w_full[sw], gn * Cfg::W_STAGE);
+                  for (int jj = 0; jj < gn; ++jj) {
+#pragma unroll
+                    for (int sb = 0; sb < 4; ++sb)
+                      bulk_g2s(w_st + sw * Cfg::W_GROUP + jj * Cfg::W_STAGE + sb * NB * 16,
+                               wsrc + (size_t)(j + jj) * Cfg::W_BLOCK + (size_t)(sb * N + prank * NB) * 16, NB * 16, &w_full[sw]);
+                  }
+                }
+                __syncwarp();
+              } else {
+                mbar_expect_tx(&w_full[sw], Cfg::W_STAGE);
+                bulk_g2s(w_st + sw * Cfg::W_STAGE, wsrc + (size_t)j * Cfg::W_BLOCK, Cfg::W_STAGE, &w_full[sw]);
+              }
               if (++sw == NW) { sw = 0; pw ^= 1; }
             }
           }
       TILE_LOOP_END
-      if (L.dbg) L.dbg[(size_t)blockIdx.x * 16 + 4] = w_e;
+      if (L.dbg && lane == 0) L.dbg[(size_t)blockIdx.x * 16 + 4] = w_e;
     }
     __syncwarp();
   } else if (warp >= 6 && warp < 14) {
@@ -291,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
           }
         }
         fence_proxy_async();
-        mbar_arrive(&a_full[sa]);
+        if constexpr (PAIR) mbar_arrive_rank<0>(&a_full[sa], 0); else mbar_arrive(&a_full[sa]);
         t_fill += clock64() - tf0;
       }
     TILE_LOOP_END
@@ -318,19 +401,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
       const int ostride = P.out_stride;
       const float* __restrict__ resid = P.resid;
       const int row_w = tau0 + quad * 32;          // first row of this warp inside M-tile 0
+      // residual registers rotate: rs[s8] of this group's NEXT chunk is requested right after rs[s8] of the current
+      // chunk has been consumed, so one set of 8 float4 covers a whole chunk iteration of load latency
       float4 rs[8];
-      auto load_resid = [&](int it, float4 (&dst)[8]) {
+      auto load_resid_row = [&](int it, int s8) -> float4 {
         const int pm = it / NCHUNK, c0 = (it - pm * NCHUNK) * 32;
         const int mt = pm % MT, ooff = P.out_off_ph[pm / MT];
-#pragma unroll
-        for (int s8 = 0; s8 < 8; ++s8) {
-          const int tau = row_w + mt * 128 + s8 * 4 + trow;
-          dst[s8] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (resid && tau < valid && c0 + tch * 4 < n_valid)
-            dst[s8] = __ldg(reinterpret_cast<const float4*>(resid + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4));
-        }
+        const int tau = row_w + mt * 128 + s8 * 4 + trow;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (resid && tau < valid && c0 + tch * 4 < n_valid)
+          v = __ldg(reinterpret_cast<const float4*>(resid + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4));
+        return v;
       };
-      if (eg < NIT) load_resid(eg, rs);
+      if (eg < NIT) {
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) rs[s8] = load_resid_row(eg, s8);
+      }
       mbar_wait_t(&tmem_full[acc], tph, L.err, 6, w_tf);
       const long long te0 = clock64();
       tc_fence_after();
@@ -358,9 +444,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             *reinterpret_cast<uint4*>(slab + lane * Cfg::EPI_PITCH + q * 16) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
         }
         __syncwarp();
-        // the accumulator registers are dead now: prefetch the residuals of this group's next chunk
-        float4 rs_next[8];
-        if (it + 2 < NIT) load_resid(it + 2, rs_next);
         const bool col_ok = !EPI || (c0 + tch * 4 < n_valid);
         float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), mu = bi, iv = make_float4(1.f, 1.f, 1.f, 1.f), of = bi;
         if (col_ok) {
@@ -387,15 +470,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
           o.x += rs[s8].x; o.y += rs[s8].y; o.z += rs[s8].z; o.w += rs[s8].w;
           if (tau < valid && col_ok)
             *reinterpret_cast<float4*>(P.out + out_base + (size_t)(tau * ostride + ooff) * out_ld + c0 + tch * 4) = o;
+          if (it + 2 < NIT) rs[s8] = load_resid_row(it + 2, s8);
         }
         __syncwarp();
-        if (it + 2 < NIT) {
-#pragma unroll
-          for (int s8 = 0; s8 < 8; ++s8) rs[s8] = rs_next[s8];
-        }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if constexpr (PAIR) mbar_arrive_rank<0>(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
       t_epi += clock64() - te0;
       if (++acc == NACC) { acc = 0; tph ^= 1; }
     TILE_LOOP_END
@@ -406,9 +486,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // nobody leaves while the peer may still signal into this CTA's shared memory
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -430,12 +514,23 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
-template <int N, int EPI, int MT, int NPH, int STK = 0>
+template <int N, int EPI, int MT, int NPH, int STK = 0, int PAIR = 0>
 int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
-  using Cfg = TcCfg<N, MT, NPH, STK>;
+  using Cfg = TcCfg<N, MT, NPH, STK, PAIR>;
   static bool attr_done = false;
+  static int max_pairs = 0;
   if (!attr_done) {
-    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, MT, NPH, STK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, MT, NPH, STK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (PAIR) {
+      cudaLaunchConfig_t qc = {};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.gridDim = dim3(ctx->sm_count & ~1); qc.blockDim = dim3(NTHREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES; qc.attrs = qa; qc.numAttrs = 1;
+      VTTS_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, tc_conv_kernel<N, EPI, MT, NPH, STK, PAIR>, &qc));
+      if (max_pairs < 1) return ctx->fail(VTTS_ERR_CUDA, "tc_conv: no CTA pair fits on this device");
+      if (max_pairs > ctx->sm_count / 2) max_pairs = ctx->sm_count / 2;
+    }
     attr_done = true;
   }
   for (int i = 0; i < L.nprob; ++i) {
@@ -451,10 +546,21 @@ int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   // static round-robin tile assignment: put the expensive problems (large k) first so that the last, partial
   // wave of tiles consists of cheap ones
   std::stable_sort(L.p, L.p + L.nprob, [](const TcProb& a, const TcProb& b) { return a.k > b.k; });
-  L.tiles_per_row = (L.T_rows + Cfg::R - 1) / Cfg::R;
+  L.tiles_per_row = (L.T_rows + Cfg::CPP * Cfg::R - 1) / (Cfg::CPP * Cfg::R);
   L.ntiles = L.nprob * L.tiles_per_row * L.B;
-  const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
-  tc_conv_kernel<N, EPI, MT, NPH, STK><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  if (PAIR) {
+    // persistent CTA pairs: clusters of two CTAs (same TPC), one pair per tile
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    const int pairs = L.ntiles < max_pairs ? L.ntiles : max_pairs;
+    lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = Cfg::SMEM_BYTES; lc.stream = st; lc.attrs = la; lc.numAttrs = 1;
+    VTTS_CUDA(cudaLaunchKernelEx(&lc, tc_conv_kernel<N, EPI, MT, NPH, STK, PAIR>, L));
+  } else {
+    const int grid = L.ntiles < ctx->sm_count ? L.ntiles : ctx->sm_count;
+    tc_conv_kernel<N, EPI, MT, NPH, STK, PAIR><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  }
   ctx->launches++;
   VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
@@ -468,13 +574,16 @@ int launch_ne(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   if constexpr (N == 256) {
     if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=256 supports single-phase tiles only");
     if (ctx->tc_variant == 0) return launch_cfg<256, EPI, 2, 1>(ctx, L, st);   // single accumulator set (slower, kept for A/B runs)
+    if (ctx->tc_variant == 3) return launch_cfg<256, EPI, 1, 1, 0, 1>(ctx, L, st);   // CTA pairs
     return launch_cfg<256, EPI, 1, 1>(ctx, L, st);
   } else if constexpr (N == 128) {
+    if (nph == 4 && ctx->tc_variant == 3) return launch_cfg<128, EPI, 1, 4, 0, 1>(ctx, L, st);
     if (nph == 4) return launch_cfg<128, EPI, 1, 4>(ctx, L, st);
     if (nph != 1) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_conv: N=128 supports 1 or 4 phases");
     if (ctx->tc_variant == 0) return launch_cfg<128, EPI, 4, 1>(ctx, L, st);
     // stacked [W_hi | W_lo]: two MMAs (N' = 256, then N' = 128) instead of three of N' = 128 per (chunk, tap, M tile)
     if (ctx->tc_variant == 2) return launch_cfg<128, EPI, 1, 1, 1>(ctx, L, st);
+    if (ctx->tc_variant == 3) return launch_cfg<128, EPI, 2, 1, 0, 1>(ctx, L, st);   // CTA pairs
     return launch_cfg<128, EPI, 2, 1>(ctx, L, st);
   } else if constexpr (N == 64) {
     if (nph == 2) return launch_cfg<64, EPI, 2, 2>(ctx, L, st);
@@ -585,6 +694,9 @@ int vtts_launch_tc_conv(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
     static int pm_env = -1;    // experiment switch: VTTS_TC_PROBLEM_MAJOR=0/1 forces the tile map of every launch
     if (pm_env < 0) { const char* e = getenv("VTTS_TC_PROBLEM_MAJOR"); pm_env = e ? atoi(e) + 1 : 0; }
     if (pm_env > 0) L.problem_major = pm_env - 1;
+    static int exp_env = -1;
+    if (exp_env < 0) { const char* e = getenv("VTTS_PAIR_EXP"); exp_env = e ? atoi(e) : 0; }
+    L.exp = exp_env;
   }
   switch (L.N) {
     case 256: return launch_n<256>(ctx, L, st);

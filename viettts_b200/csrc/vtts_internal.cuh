@@ -111,6 +111,8 @@ struct TcLaunch {
                               // the others: generator 19.8 -> 19.1 ms.  1: problems back to back (experiments only)
   int* err;                   // device int: set before trapping on a barrier timeout
   long long* dbg;             // optional [grid][16] per-role stall counters (vtts_debug_tc_stats)
+  int exp;                    // experiment bits of the CTA-pair form (VTTS_PAIR_EXP; 0 in production): 1 = the issuer polls with
+                              // test_wait instead of try_wait, 4 = cluster-scope release on the weight forwarder's arrive (slow)
 };
 
 // ---- fused ResBlock pair (tc_pair.cu): out = conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x, C = N channels ----
@@ -145,7 +147,7 @@ struct vtts_ctx {
   bool tc_dbg_on = false;
   int fuse_pairs = 1;              // 1 = ResBlock pairs with C <= 64 run in a fused pair kernel (intermediate stays on chip: 8 instead of 20 B of HBM traffic per element pair)
   int pair_ts = 2;                 // fused pair kernel: 0 tc_pair.cu (one issuer, smem operand), 1 tc_pair_ts.cu (operand in TMEM), 2 tc_pair2.cu (two decoupled pipelines, smem operand)
-  int tc_variant = 1;              // tile-shape variant of the tensor-core conv (see TcCfg); 1 = double-buffered accumulators for N >= 128
+  int tc_variant = 3;              // tile-shape variant of the tensor-core conv (see TcCfg): 3 = CTA pairs (cta_group::2) for N >= 128 (default), 1 = single-CTA form, 0 / 2 = older experiments
   void* hg_wpk = nullptr;       // packed tensor-core weights of the 72 resblock convs
   std::vector<void*> hg_wpk_t;
   std::vector<void*> hg_wpk_ups;   // [stage][phase] packed transposed-conv phase weights
