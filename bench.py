@@ -625,7 +625,7 @@ def run_ours(args):
                                           note="same call with a plain numpy result array (the reference's return type): one more host copy")),
             gpu_launches=int(launches),
             roofline=dict(bound="tensor",
-                          kernel=("tcgen05 conv kernels of the generator (tc_conv_kernel + tc_pair_ts_kernel), all launches of one step (+ conv_post, 1 % of the stage time)"
+                          kernel=("tcgen05 conv kernels of the generator (tc_conv_kernel, CTA-pair form for C >= 128, + tc_pair2_kernel), all launches of one step (+ conv_post, 1 % of the stage time)"
                                   if args.precision != "fp32" else "conv1d_nwc_kernel: the generator launches of one step (+ conv_post)"),
                           achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_tflops_sustained"],
                           traffic=traffic, traffic_source=traffic_src,

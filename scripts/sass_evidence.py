@@ -8,7 +8,7 @@ from pathlib import Path
 
 REPO = Path(__file__).resolve().parents[1]
 LIB = REPO / "viettts_b200" / "libviettts_b200.so"
-PAT = {"UTCHMMA": r"\bUTCHMMA\b", "UTCQMMA/other UTC*MMA": r"\bUTC[A-Z]*MMA\b", "UTCBAR (tcgen05.commit)": r"\bUTCBAR\b", "LDTM (tcgen05.ld)": r"\bLDTM\b",
+PAT = {"UTCHMMA": r"\bUTCHMMA\b", "UTCHMMA.2CTA (cta_group::2)": r"\bUTCHMMA\.2CTA\b", "UTCBAR.2CTA.MULTICAST": r"\bUTCBAR\.2CTA\S*MULTICAST\b", "UTCQMMA/other UTC*MMA": r"\bUTC[A-Z]*MMA\b", "UTCBAR (tcgen05.commit)": r"\bUTCBAR\b", "LDTM (tcgen05.ld)": r"\bLDTM\b",
        "STTM (tcgen05.st)": r"\bSTTM\b", "UTCCP (tcgen05.cp)": r"\bUTCCP\b", "UBLKCP (cp.async.bulk)": r"\bUBLKCP\b", "UTMALDG/UTMASTG (tensor TMA)": r"\bUTMA(LDG|STG)\b",
        "SYNCS (mbarrier)": r"\bSYNCS\b", "HMMA (legacy mma.sync)": r"\bHMMA\b", "HGMMA (wgmma)": r"\bHGMMA\b", "FFMA": r"\bFFMA\b"}
 
