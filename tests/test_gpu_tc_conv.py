@@ -151,3 +151,51 @@ def test_fused_pair_long_rows_many_tiles(eng):
             n = lens[bb]
             ref = _ref_pair(x[bb : bb + 1, :n], w1, b1, w2, b2, k, dil, 0.1)
             assert np.abs(out[bb, :n] - ref[0]).max() < 3e-4, (C, k, dil, bb)
+
+
+@pytest.mark.parametrize("C", [128, 256])
+def test_cta_pair_and_single_cta_conv_are_bit_identical(eng, C):
+    """C >= 128 runs as CTA pairs (tcgen05 cta_group::2, tc_variant 3, the default) or as single CTAs (tc_variant 1):
+    the same products in the same order, so the two forms must agree BIT FOR BIT -- on more pair tiles than clusters
+    (every ring wraps), with lengths that end inside the first / second CTA's half of a pair tile, an empty second
+    half, and a row shorter than the conv's halo."""
+    dev = torch.device("cuda", 0)
+    R2 = 512 if C == 128 else 256                      # rows of a pair tile
+    B, T = 6, 40 * R2 + 77
+    lens = np.array([T, 39 * R2 + 5, 17 * R2 + R2 // 2 + 3, 3 * R2, R2 // 2, 4], np.int32)
+    try:
+        for k, dil in ((3, 1), (7, 3), (11, 5)):
+            rng = np.random.default_rng(C + k)
+            x = torch.from_numpy(rng.standard_normal((B, T, C)).astype(np.float32)).to(dev)
+            res = torch.from_numpy(rng.standard_normal((B, T, C)).astype(np.float32)).to(dev)
+            w = torch.from_numpy((rng.standard_normal((k, C, C)) / np.sqrt(k * C)).astype(np.float32)).to(dev)
+            b = torch.from_numpy((rng.standard_normal(C) * 0.1).astype(np.float32)).to(dev)
+            ln = torch.from_numpy(lens).to(dev)
+            outs = {}
+            for variant in (1, 3):
+                eng.tc_stats(False, variant=variant)
+                outs[variant] = eng.debug_conv1d("bf16x3", x, w, b, k, dil, 0.1, res, ln).cpu().numpy()
+            for bb in range(B):
+                n = lens[bb]
+                assert np.array_equal(outs[1][bb, :n], outs[3][bb, :n]), (C, k, dil, bb)
+            # and the pair form against float64 on the rows that straddle tile boundaries
+            xs, rs = x.cpu().numpy(), res.cpu().numpy()
+            for bb in (2, 4, 5):
+                n = lens[bb]
+                ref = _ref_conv(xs[bb : bb + 1, :n], w.cpu().numpy(), b.cpu().numpy(), k, dil, 0.1, rs[bb : bb + 1, :n])
+                assert np.abs(outs[3][bb, :n] - ref[0]).max() < 2e-4, (C, k, dil, bb)
+    finally:
+        eng.tc_stats(False, variant=3)
+
+
+def test_generator_same_waveform_in_both_conv_forms(eng):
+    mel = synthetic.mel_input(33, 3, 70)
+    nf = np.array([70, 41, 9], np.int32)
+    try:
+        eng.tc_stats(False, variant=1)
+        a = eng.mel2wave(mel, n_frames=nf)
+        eng.tc_stats(False, variant=3)
+        b = eng.mel2wave(mel, n_frames=nf)
+    finally:
+        eng.tc_stats(False, variant=3)
+    assert np.array_equal(a, b)

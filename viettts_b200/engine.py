@@ -121,7 +121,8 @@ class Engine:
 
     def tc_stats(self, enable=True, variant=None):
         """Per-CTA stall counters of the last tensor-core conv launch (see vtts_debug_tc_stats);
-        `variant` (0/1) optionally selects the tile-shape variant for later launches."""
+        `variant` optionally selects the conv form for later launches: 3 = CTA pairs (cta_group::2) for C >= 128 (default),
+        1 = single-CTA form, 0 / 2 = older tile-shape experiments."""
         out = np.zeros((256, 16), np.int64)
         flags = (1 if enable else 0) | (0 if variant is None else (0x100 | (int(variant) << 4)))
         self._ck(self.lib.vtts_debug_tc_stats(self.h, flags, _ptr(out)))

@@ -55,7 +55,8 @@ ROW_US_PER_FRAME = 1.9
 def batch_cost_us(n_frames_of_rows) -> float:
     n = np.asarray(n_frames_of_rows, dtype=np.int64)
     rows = len(n)
-    scans = (rows + 31) // 32                         # the decoder scan takes up to 32 rows per launch
+    scans = (rows + 31) // 32                         # row groups of 32 (one launch takes up to 4; they share its barriers, so this
+                                                      # over-estimates > 32 rows by ~10 %: balanced_buckets keeps buckets <= 32 rows)
     return float(n.max()) * (SCAN_US_PER_FRAME * scans + SCAN_US_PER_FRAME_ROW * rows + ROW_US_PER_FRAME * rows)
 
 
