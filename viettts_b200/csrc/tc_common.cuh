@@ -194,6 +194,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// read-only 16 B load that asks L2 to fetch the whole 256 B block around it: the converters read 64 B of every 512 B (or
+// 256 B, 128 B) activation row per 16-channel chunk, so the next three chunks of the same rows then hit L2 instead of DRAM
+__device__ __forceinline__ float4 ldg_pf256(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // leaky_relu for 0 < s < 1: max(v, s*v) (2 instructions; identical to v >= 0 ? v : s*v for every finite v and +-0)
 __device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, s * v); }
 

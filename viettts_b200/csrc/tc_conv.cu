@@ -347,10 +347,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const __grid_const
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rr < rows && t >= 0 && t < valid) {
               const size_t off = (size_t)t * ld + coff;
-              v[u] = __ldg(reinterpret_cast<const float4*>(x0 + off));
+              v[u] = ldg_pf256(x0 + off);
               if (pre_mode == 2) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(x1 + off));
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(x2 + off));
+                const float4 a = ldg_pf256(x1 + off);
+                const float4 bb = ldg_pf256(x2 + off);
                 v[u].x = ((v[u].x + a.x) + bb.x) / 3.0f;
                 v[u].y = ((v[u].y + a.y) + bb.y) / 3.0f;
                 v[u].z = ((v[u].z + a.z) + bb.z) / 3.0f;

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
             const int rr = rr0 + u * 32;
             const int t = row_base + rr;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rr < rows && t >= 0 && t < valid) v[u] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)t * N + coff));
+            if (rr < rows && t >= 0 && t < valid) v[u] = ldg_pf256(x0 + (size_t)t * N + coff);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
