@@ -664,7 +664,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep and the strict-fp32 line")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[3] / configs[4]")
     ap.add_argument("--c5-groups", type=int, default=0, help="equal-cost buckets per rank of the mixed-length workload (0 = pick 2..4 by predicted makespan)")
-    ap.add_argument("--pairs", default="auto", choices=["auto", "off", "smem2", "tmem", "smem"],
+    ap.add_argument("--pairs", default="auto", choices=["auto", "off", "smem2", "smem2c", "tmem", "smem"],
                     help="C<=64 ResBlock pairs: auto = library default, off = two conv launches per pair, tmem / smem = fused pair kernel "
                          "with the A operand in tensor memory / shared memory")
     ap.add_argument("--tc-variant", type=int, default=None, help="tile-shape variant of tc_conv (tuning aid; default: library default)")

@@ -95,7 +95,7 @@ def _ref_pair(x, w1, b1, w2, b2, k, dil, slope):
     return (y.transpose(1, 2) + xt).numpy()
 
 
-@pytest.mark.parametrize("ts", ["smem2", "tmem", "smem"])
+@pytest.mark.parametrize("ts", ["smem2", "smem2c", "tmem", "smem"])
 @pytest.mark.parametrize("C", [32, 64])
 @pytest.mark.parametrize("k,dil", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
 def test_fused_pair_vs_float64(eng, C, k, dil, ts):
@@ -120,7 +120,7 @@ def test_fused_pair_vs_float64(eng, C, k, dil, ts):
         assert err < 3e-4, (C, k, dil, bb, err)
 
 
-@pytest.mark.parametrize("ts", ["smem2", "tmem", "smem"])
+@pytest.mark.parametrize("ts", ["smem2", "smem2c", "tmem", "smem"])
 def test_fused_and_unfused_generator_agree(eng, hifigan_params, ts):
     mel = synthetic.mel_input(21, 2, 50)
     nf = np.array([50, 31], np.int32)
@@ -135,7 +135,8 @@ def test_fused_pair_long_rows_many_tiles(eng):
     """More tiles than SMs (the persistent loop wraps, every ring changes phase many times) and a length that ends
     inside a tile; C = 32 and 64 at the generator's own kernel sizes."""
     dev = torch.device("cuda", 0)
-    for kind, C, k, dil in (("smem2", 32, 7, 3), ("smem2", 64, 11, 5), ("smem2", 64, 3, 1), ("tmem", 32, 11, 5), ("tmem", 64, 7, 3)):
+    for kind, C, k, dil in (("smem2", 32, 7, 3), ("smem2", 64, 11, 5), ("smem2", 64, 3, 1), ("tmem", 32, 11, 5), ("tmem", 64, 7, 3),
+                            ("smem2c", 32, 7, 3), ("smem2c", 64, 11, 5), ("smem2c", 64, 3, 1), ("smem2c", 32, 3, 1)):
         eng.set_fused_pairs(False, kind=kind)
         rng = np.random.default_rng(C + k)
         B, T = 4, 9000

@@ -397,14 +397,17 @@ int vtts_debug_pair(vtts_ctx* ctx, const float* x_dev, const float* w1_dev, cons
   VTTS_CUDA(cudaSetDevice(ctx->device));
   void* wpk = nullptr;
   const size_t bytes = vtts_tc_packed_elems(k, C, C) * 2;
-  VTTS_CUDA(cudaMalloc(&wpk, 2 * bytes));
+  const size_t cb = (vtts_tc_packed_pc_bytes(k, C) + 255) & ~size_t(255);
+  VTTS_CUDA(cudaMalloc(&wpk, 2 * bytes + 2 * cb));
   int rc = vtts_tc_pack_weights(ctx, w1_dev, wpk, k, C, C, 0, C);
   if (!rc) rc = vtts_tc_pack_weights(ctx, w2_dev, (char*)wpk + bytes, k, C, C, 0, C);
+  if (!rc) rc = vtts_tc_pack_weights_pc(ctx, w1_dev, (char*)wpk + 2 * bytes, k, C);
+  if (!rc) rc = vtts_tc_pack_weights_pc(ctx, w2_dev, (char*)wpk + 2 * bytes + cb, k, C);
   if (rc) { cudaFree(wpk); return rc; }
   TcPairLaunch PL;
   memset(&PL, 0, sizeof(PL));
   PL.nprob = 1; PL.N = C; PL.B = B; PL.T_rows = T; PL.len = len_dev; PL.len_mul = 1; PL.slope = slope;
-  PL.p[0] = TcPairProb{x_dev, wpk, (char*)wpk + bytes, b1_dev, b2_dev, out_dev, k, dil};
+  PL.p[0] = TcPairProb{x_dev, wpk, (char*)wpk + bytes, b1_dev, b2_dev, out_dev, k, dil, (char*)wpk + 2 * bytes, (char*)wpk + 2 * bytes + cb};
   rc = vtts_launch_tc_pair(ctx, PL, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(wpk);

@@ -420,6 +420,7 @@ int launch_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
 int vtts_launch_tc_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
   if (ctx->pair_ts == 1) return vtts_launch_tc_pair_ts(ctx, L, st);
   if (ctx->pair_ts == 2) return vtts_launch_tc_pair2(ctx, L, st);
+  if (ctx->pair_ts == 3) return vtts_launch_tc_pair2c(ctx, L, st);
   if (L.nprob < 1 || L.nprob > 3) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_pair: nprob %d", L.nprob);
   for (int i = 0; i < L.nprob; ++i) {
     const TcPairProb& p = L.p[i];

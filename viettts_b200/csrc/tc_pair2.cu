@@ -38,8 +38,15 @@ constexpr int W_E2 = 4, W_ISSA = 12, W_ISSB = 13, W_WP1 = 14, W_WP2 = 15, W_CONV
 constexpr int NGRP = 3, GRP_THREADS = 128;
 constexpr int NA = 4;              // conv1 activation stages (one 16-channel chunk each)
 
-template <int N>
+// PAIR = 1: the CTA-pair form (cf. tc_conv.cu): a cluster of two CTAs works on two tiles of the SAME problem, rank 0 issues
+// `tcgen05.mma.cta_group::2` (M = 256: rank r's 128 rows are its own tile) and each CTA holds only its half of the
+// weight operand:  MMA 1 (N' = 2N):  rank 0 supplies W_hi, rank 1 W_lo;   MMA 2 (N' = N): rank r supplies W_hi[rN/2, (r+1)N/2).
+// The weights come pre-packed per rank ([chunk][rank][tap][k-half][N rows | N/2 rows][8], vtts_tc_pack_weights_pc), so a
+// group of taps is still ONE bulk copy per CTA; shared-memory operand bytes per product: 11 instead of 14 KB at C = 64.
+template <int N, int PAIR_ = 0>
 struct P2Cfg {
+  static constexpr int PAIR = PAIR_;
+  static constexpr int CPP = PAIR ? 2 : 1;
   static constexpr int MT = N == 64 ? 1 : 2;
   static constexpr int R = 128 * MT;
   static constexpr int G = 4;                        // taps per weight group (one bulk copy, one issue region)
@@ -49,7 +56,8 @@ struct P2Cfg {
   static constexpr int A1_STAGE = RA1 * 64;
   static constexpr int A2_CHUNK = RA2 * 64;
   static constexpr int A2_BUF = NCH * A2_CHUNK;
-  static constexpr int W_STAGE = N * 64;             // one (chunk, tap): [k-half][hi|lo][n][8 bf16]
+  static constexpr int W_STAGE = PAIR ? N * 48 : N * 64;   // one (chunk, tap): [k-half][hi|lo][n][8 bf16]; pair form: [k-half][N | N/2 rows][8]
+  static constexpr int KH_ROWS = PAIR ? N + N / 2 : 2 * N;  // rows of one k-half block
   static constexpr int W_GROUP = G * W_STAGE;
   static constexpr int NWG = N == 64 ? 2 : 3;        // weight groups in flight per ring
   static constexpr int EPI_PITCH = 80;               // 16 floats + 16 B pad
@@ -61,9 +69,13 @@ struct P2Cfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
-template <bool PROF>
+// CL = 1: acquire at cluster scope (barriers of the pair form whose arrivals come from both CTAs)
+template <bool PROF, int CL = 0>
 __device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc) {
-  if constexpr (PROF) {
+  if constexpr (CL) {
+    long long dummy = 0;
+    mbar_wait_tc<0>(bar, parity, err, code, PROF ? acc : dummy);
+  } else if constexpr (PROF) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
       if (clock64() - t0 > SPIN_TIMEOUT) spin_fail(err, code);
@@ -78,10 +90,11 @@ __device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity, int*
   }
 }
 
-template <int N, bool PROF>
+template <int N, bool PROF, int PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_constant__ TcPairLaunch L) {
-  using Cfg = P2Cfg<N>;
+  using Cfg = P2Cfg<N, PAIR>;
   constexpr int MT = Cfg::MT, R = Cfg::R, G = Cfg::G, NCH = Cfg::NCH, RA1 = Cfg::RA1, RA2 = Cfg::RA2, NWG = Cfg::NWG;
+  constexpr int CPP = Cfg::CPP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a1_st = smem;
@@ -101,21 +114,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  // pair form: every barrier an issuer waits on lives in rank 0 and counts the arrivals of both CTAs (rank 1 arrives
+  // through the cluster address space); the *_empty / d_full barriers are signalled in both CTAs by multicast commits
+  const uint32_t prank = PAIR ? cluster_rank() : 0u;
 
   if (warp == W_WP1 && lane == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a1_full[i], GRP_THREADS); mbar_init(&a1_empty[i], 1); }
-    for (int i = 0; i < 2 * NWG; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a1_full[i], CPP * GRP_THREADS); mbar_init(&a1_empty[i], 1); }
+    for (int i = 0; i < 2 * NWG; ++i) { mbar_init(&w_full[i], (PAIR && prank == 0) ? 2 : 1); mbar_init(&w_empty[i], 1); }
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
-    mbar_init(&d_empty[0], 128); mbar_init(&d_empty[1], 256);
-    for (int i = 0; i < 2; ++i) { mbar_init(&a2_full[i], 128); mbar_init(&a2_empty[i], 1); }
+    mbar_init(&d_empty[0], CPP * 128); mbar_init(&d_empty[1], CPP * 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a2_full[i], CPP * 128); mbar_init(&a2_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_ISSA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -123,33 +145,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
 // tile -> problem map: round robin (problem = tile % nprob), so row tile r of every problem is in flight at the same time
 // and a tensor the problems SHARE (the three ResBlocks of a stage read the same input in their first pair) is fetched
 // from DRAM once and served from L2 to the others; problems with fewer tiles (larger V) skip their surplus indices.
+// Pair form: tile index -> two consecutive tiles (rest = 2 q + rank) of one problem; a CTA whose own tile does not exist or
+// lies beyond its row's length still walks the pipeline with valid = 0 (zero operand, no stores) as long as its peer's
+// tile is live -- the skip decision must be the same in both CTAs.
 #define P2_TILE_BEGIN                                                                 \
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {                     \
+  for (int tile = blockIdx.x / CPP; tile < ntiles; tile += gridDim.x / CPP) {         \
     const int pi = tile % L.nprob;                                                    \
     const TcPairProb& P = L.p[pi];                                                    \
-    const int rest = tile / L.nprob;                                                  \
     const int tpr = L.tiles_per_row[pi];                                              \
-    if (rest >= tpr * L.B) continue;                                                  \
-    const int tt = rest % tpr;                                                        \
-    const int b = rest / tpr;                                                         \
     const int k = P.k, dil = P.dil;                                                   \
     const int V = R - (k - 1);                                                        \
-    const int o0 = tt * V;                                                            \
-    int valid = L.T_rows;                                                             \
-    if (L.len) {                                                                      \
-      const int v_ = L.len[b] * L.len_mul;                                            \
-      valid = v_ < valid ? v_ : valid;                                                \
+    int tt, b, o0, valid;                                                             \
+    if constexpr (PAIR) {                                                             \
+      bool any_live = false;                                                          \
+      tt = 0; b = 0; o0 = 0; valid = 0;                                               \
+      _Pragma("unroll") for (int rk = 0; rk < 2; ++rk) {                              \
+        const int rest_ = (tile / L.nprob) * 2 + rk;                                  \
+        int tt_ = 0, b_ = 0, valid_ = 0;                                              \
+        if (rest_ < tpr * L.B) {                                                      \
+          tt_ = rest_ % tpr;                                                          \
+          b_ = rest_ / tpr;                                                           \
+          valid_ = L.T_rows;                                                          \
+          if (L.len) {                                                                \
+            const int v_ = L.len[b_] * L.len_mul;                                     \
+            valid_ = v_ < valid_ ? v_ : valid_;                                       \
+          }                                                                           \
+          if (tt_ * V >= valid_) valid_ = 0;                                          \
+        }                                                                             \
+        any_live |= valid_ > 0;                                                       \
+        if (rk == (int)prank) { tt = tt_; b = b_; o0 = tt_ * V; valid = valid_; }     \
+      }                                                                               \
+      if (!any_live) continue;                                                        \
+    } else {                                                                          \
+      const int rest = tile / L.nprob;                                                \
+      if (rest >= tpr * L.B) continue;                                                \
+      tt = rest % tpr;                                                                \
+      b = rest / tpr;                                                                 \
+      o0 = tt * V;                                                                    \
+      valid = L.T_rows;                                                               \
+      if (L.len) {                                                                    \
+        const int v_ = L.len[b] * L.len_mul;                                          \
+        valid = v_ < valid ? v_ : valid;                                              \
+      }                                                                               \
+      if (o0 >= valid) continue;                                                      \
     }                                                                                 \
-    if (o0 >= valid) continue;                                                        \
     const int h2 = (k - 1) / 2, h1 = ((k - 1) * dil) / 2;                             \
     const int ng = (k + G - 1) / G;
 #define P2_TILE_END }
 
-  if (warp == W_ISSA || warp == W_ISSB) {
+  if ((warp == W_ISSA || warp == W_ISSB) && PAIR && prank != 0) {
+    // ============================ pair form, rank 1: weight-group forwarders (one per ring) ============================
+    // this CTA's half of a weight group lands on its own w_full; tell the issuer of that ring in rank 0
+    const int ring = warp == W_ISSA ? 0 : 1;
+    uint32_t ws = 0, wph = 0;
+    long long c_w = 0;
+    P2_TILE_BEGIN
+      (void)b; (void)h1; (void)h2; (void)o0; (void)tt; (void)dil; (void)V; (void)valid;
+      for (int s_ = 0; s_ < NCH * ng; ++s_) {
+        mbar_wait_p<PROF>(&w_full[ring * NWG + ws], wph, L.err, 34 + ring, c_w);
+        if (elect_one()) mbar_arrive_rank<0>(&w_full[ring * NWG + ws], 0);
+        __syncwarp();
+        if (++ws == NWG) { ws = 0; wph ^= 1; }
+      }
+    P2_TILE_END
+  } else if (warp == W_ISSA || warp == W_ISSB) {
     // ============================ MMA issuers: ring 0 = conv1, ring 1 = conv2 ============================
     const int ring = warp == W_ISSA ? 0 : 1;
-    constexpr uint32_t idesc = make_idesc(N), idesc2 = make_idesc(2 * N);
-    const uint64_t b_tmpl = make_desc(0, 2 * N * 16, 128);          // [k-half][hi|lo][n][8]: k-half blocks 2N rows apart
+    constexpr uint32_t idesc = PAIR ? make_idesc2(N) : make_idesc(N), idesc2 = PAIR ? make_idesc2(2 * N) : make_idesc(2 * N);
+    const uint64_t b_tmpl = make_desc(0, Cfg::KH_ROWS * 16, 128);   // [k-half][hi|lo][n][8]: k-half blocks 2N rows apart (pair form: 1.5 N)
     const uint64_t a_tmpl = make_desc(0, (ring == 0 ? RA1 : RA2) * 16, 128);
     const uint32_t RAx = ring == 0 ? RA1 : RA2;
     const uint32_t w_ring_u32 = smem_u32(w_st + (size_t)ring * NWG * Cfg::W_GROUP);
@@ -159,16 +222,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
     long long c_d = 0, c_a = 0, c_w = 0;
     const long long t_begin = PROF ? clock64() : 0;
     P2_TILE_BEGIN
-      (void)b; (void)h1; (void)h2; (void)o0;
+      (void)b; (void)h1; (void)h2; (void)o0; (void)tt; (void)V; (void)valid;
       const int dl = ring == 0 ? dil : 1;
-      mbar_wait_p<PROF>(&d_empty[ring], dph ^ 1, L.err, 30 + ring, c_d);
-      if (ring == 1) mbar_wait_p<PROF>(&a2_full[buf], bph, L.err, 32, c_a);
+      mbar_wait_p<PROF, PAIR>(&d_empty[ring], dph ^ 1, L.err, 30 + ring, c_d);
+      if (ring == 1) mbar_wait_p<PROF, PAIR>(&a2_full[buf], bph, L.err, 32, c_a);
       tc_fence_after();
       for (int c = 0; c < NCH; ++c) {
         uint32_t a_base16, sa = 0;
         if (ring == 0) {
           sa = item % NA;
-          mbar_wait_p<PROF>(&a1_full[sa], (item / NA) & 1, L.err, 33, c_a);
+          mbar_wait_p<PROF, PAIR>(&a1_full[sa], (item / NA) & 1, L.err, 33, c_a);
           tc_fence_after();
           a_base16 = (a1_u32 + sa * Cfg::A1_STAGE) >> 4;
           ++item;
@@ -177,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
         }
         for (int g = 0; g < ng; ++g) {
           const int nt = (k - g * G) < G ? (k - g * G) : G;
-          mbar_wait_p<PROF>(&w_full[ring * NWG + ws], wph, L.err, 34 + ring, c_w);
+          mbar_wait_p<PROF, PAIR>(&w_full[ring * NWG + ws], wph, L.err, 34 + ring, c_w);
           tc_fence_after();
           const uint32_t w_base16 = (w_ring_u32 + ws * Cfg::W_GROUP) >> 4;
           const uint32_t first_grp = (c | g) != 0 ? 1u : 0u;
@@ -190,23 +253,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
                 const uint64_t a_hi = a_tmpl | (uint64_t)row;
                 const uint64_t a_lo = a_tmpl | (uint64_t)(row + 2 * RAx);
                 const uint32_t d = d0 + mt * 2 * N;
-                umma<0>(d, a_hi, b_hi, idesc2, (first_grp | (uint32_t)t) != 0 ? 1u : 0u);   // [main | aux] (+)= a_hi . [W_hi | W_lo]
-                umma<0>(d, a_lo, b_hi, idesc, 1u);                                           //  main        += a_lo . W_hi
+                if constexpr (PAIR) {
+                  // rows [0, N) of the k-half block: this rank's half of [W_hi | W_lo]; rows [N, 1.5 N): its half of W_hi
+                  umma2<0>(d, a_hi, b_hi, idesc2, (first_grp | (uint32_t)t) != 0 ? 1u : 0u);
+                  umma2<0>(d, a_lo, b_hi + N, idesc, 1u);
+                } else {
+                  umma<0>(d, a_hi, b_hi, idesc2, (first_grp | (uint32_t)t) != 0 ? 1u : 0u);   // [main | aux] (+)= a_hi . [W_hi | W_lo]
+                  umma<0>(d, a_lo, b_hi, idesc, 1u);                                           //  main        += a_lo . W_hi
+                }
               }
             }
-            umma_commit(&w_empty[ring * NWG + ws]);
+            if constexpr (PAIR) umma_commit2(&w_empty[ring * NWG + ws]); else umma_commit(&w_empty[ring * NWG + ws]);
           }
           __syncwarp();
           if (++ws == NWG) { ws = 0; wph ^= 1; }
         }
         if (ring == 0) {
-          if (elect_one()) umma_commit(&a1_empty[sa]);
+          if (elect_one()) { if constexpr (PAIR) umma_commit2(&a1_empty[sa]); else umma_commit(&a1_empty[sa]); }
           __syncwarp();
         }
       }
       if (elect_one()) {
-        if (ring == 1) umma_commit(&a2_empty[buf]);
-        umma_commit(&d_full[ring]);
+        if constexpr (PAIR) {
+          if (ring == 1) umma_commit2(&a2_empty[buf]);
+          umma_commit2(&d_full[ring]);
+        } else {
+          if (ring == 1) umma_commit(&a2_empty[buf]);
+          umma_commit(&d_full[ring]);
+        }
       }
       __syncwarp();
       dph ^= 1;
@@ -224,15 +298,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
       uint32_t ws = 0, wph = 0;
       long long c_e = 0;
       P2_TILE_BEGIN
-        (void)b; (void)h1; (void)h2; (void)o0; (void)dil;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(ring == 0 ? P.w1pk : P.w2pk);
+        (void)b; (void)h1; (void)h2; (void)o0; (void)dil; (void)tt; (void)V; (void)valid;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(PAIR ? (ring == 0 ? P.w1pc : P.w2pc) : (ring == 0 ? P.w1pk : P.w2pk));
         for (int c = 0; c < NCH; ++c)
           for (int g = 0; g < ng; ++g) {
             const int nt = (k - g * G) < G ? (k - g * G) : G;
             const uint32_t bytes = (uint32_t)nt * Cfg::W_STAGE;
             mbar_wait_p<PROF>(&w_empty[ring * NWG + ws], wph ^ 1, L.err, 36 + ring, c_e);
             mbar_expect_tx(&w_full[ring * NWG + ws], bytes);
-            bulk_g2s(wr + ws * Cfg::W_GROUP, wsrc + ((size_t)c * k + (size_t)g * G) * Cfg::W_STAGE, bytes, &w_full[ring * NWG + ws]);
+            // pair form: blocks are ordered [chunk][rank][tap], so this rank's taps of a chunk are contiguous as well
+            const size_t blk = PAIR ? ((size_t)(c * 2 + (int)prank) * k + (size_t)g * G) : ((size_t)c * k + (size_t)g * G);
+            bulk_g2s(wr + ws * Cfg::W_GROUP, wsrc + blk * Cfg::W_STAGE, bytes, &w_full[ring * NWG + ws]);
             if (++ws == NWG) { ws = 0; wph ^= 1; }
           }
       P2_TILE_END
@@ -250,7 +326,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
     long long c_e = 0;
     const long long t_begin = PROF ? clock64() : 0;
     P2_TILE_BEGIN
-      (void)ng;
+      (void)ng; (void)tt; (void)V;
       const int rows = R + (k - 1) * dil;
       const float* x0 = P.x + (size_t)b * L.T_rows * N;
       const int row_base = o0 - h2 - h1;
@@ -284,7 +360,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
           }
         }
         fence_proxy_async();                                   // generic-proxy stores -> visible to the tensor core's operand fetch
-        mbar_arrive(&a1_full[sa]);
+        if constexpr (PAIR) mbar_arrive_rank<0>(&a1_full[sa], 0); else mbar_arrive(&a1_full[sa]);
       }
     P2_TILE_END
     if (PROF && L.dbg && gt == 0 && blockIdx.x < 128) {
@@ -299,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
     long long c_df = 0, c_ae = 0;
     const long long t_begin = PROF ? clock64() : 0;
     P2_TILE_BEGIN
-      (void)b; (void)h1; (void)dil; (void)ng; (void)V;
+      (void)b; (void)h1; (void)dil; (void)ng; (void)V; (void)tt;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
       mbar_wait_p<PROF>(&d_full[0], dph, L.err, 44, c_df);
       mbar_wait_p<PROF>(&a2_empty[buf], bph ^ 1, L.err, 45, c_ae);
@@ -321,7 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
         }
         if (half == 1) {
           tc_fence_before();
-          mbar_arrive(&d_empty[0]);                            // D1 is in registers: conv1 of the next tile may start
+          if constexpr (PAIR) mbar_arrive_rank<0>(&d_empty[0], 0); else mbar_arrive(&d_empty[0]);   // D1 is in registers: conv1 of the next tile may start
         }
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
@@ -353,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
         }
       }
       fence_proxy_async();                                     // conv2 operand: generic-proxy stores -> tensor core
-      mbar_arrive(&a2_full[buf]);
+      if constexpr (PAIR) mbar_arrive_rank<0>(&a2_full[buf], 0); else mbar_arrive(&a2_full[buf]);
       dph ^= 1;
       if (++buf == 2) { buf = 0; bph ^= 1; }
     P2_TILE_END
@@ -372,7 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
     long long c_df = 0;
     const long long t_begin = PROF ? clock64() : 0;
     P2_TILE_BEGIN
-      (void)h1; (void)h2; (void)dil; (void)ng;
+      (void)h1; (void)h2; (void)dil; (void)ng; (void)tt;
       const size_t base = (size_t)b * L.T_rows * N;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + Cfg::ACC;
       float4 rs[2][4];
@@ -403,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
         for (int i = 0; i < 16; ++i) r[sub][i] = __float_as_uint(__uint_as_float(r[sub][i]) + __uint_as_float(ax[i]));
       }
       tc_fence_before();
-      mbar_arrive(&d_empty[1]);                                // D2 is in registers: conv2 of the next tile may start
+      if constexpr (PAIR) mbar_arrive_rank<0>(&d_empty[1], 0); else mbar_arrive(&d_empty[1]);   // D2 is in registers: conv2 of the next tile may start
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const int it = 2 * eh + sub;
@@ -437,21 +513,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair2_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // nobody leaves while the peer may still signal into this CTA's shared memory
   if (warp == W_ISSA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
-template <int N>
+// fp32 Haiku conv weight w[k][C][C] -> CTA-pair layout: [chunk c = C/16][rank][tap j][k-half][1.5 C rows][8 bf16]
+//   rank 0 rows: W_hi[0, C)  then W_hi[0, C/2)        (its halves of [W_hi | W_lo] and of W_hi)
+//   rank 1 rows: W_lo[0, C)  then W_hi[C/2, C)
+__global__ void pack_w_pc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int k, int C) {
+  const int rows = C + C / 2;
+  const size_t total = (size_t)(C / 16) * 2 * k * 2 * rows * 8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r_ = idx;
+    const int e = r_ % 8; r_ /= 8;
+    const int q = r_ % rows; r_ /= rows;
+    const int kh = r_ % 2; r_ /= 2;
+    const int j = r_ % k; r_ /= k;
+    const int rank = r_ % 2; r_ /= 2;
+    const int c = (int)r_;
+    int n, lo;
+    if (q < C) { n = q; lo = rank; }
+    else { n = (q - C) + rank * (C / 2); lo = 0; }
+    const int i = c * 16 + kh * 8 + e;
+    const float v = w[((size_t)j * C + i) * C + n];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[idx] = lo ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
+}
+
+template <int N, int PAIR = 0>
 int launch_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
-  using Cfg = P2Cfg<N>;
+  using Cfg = P2Cfg<N, PAIR>;
   static bool attr_done = false;
+  static int max_pairs = 0;
   if (!attr_done) {
-    VTTS_CUDA(cudaFuncSetAttribute(tc_pair2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    VTTS_CUDA(cudaFuncSetAttribute(tc_pair2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_pair2_kernel<N, false, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VTTS_CUDA(cudaFuncSetAttribute(tc_pair2_kernel<N, true, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (PAIR) {
+      cudaLaunchConfig_t qc = {};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.gridDim = dim3(ctx->sm_count & ~1); qc.blockDim = dim3(NTHREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES; qc.attrs = qa; qc.numAttrs = 1;
+      VTTS_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, tc_pair2_kernel<N, false, PAIR>, &qc));
+      if (max_pairs < 1) return ctx->fail(VTTS_ERR_CUDA, "tc_pair2: no CTA pair fits on this device");
+      if (max_pairs > ctx->sm_count / 2) max_pairs = ctx->sm_count / 2;
+    }
     attr_done = true;
   }
+  if (PAIR)
+    for (int i = 0; i < L.nprob; ++i)
+      if (!L.p[i].w1pc || !L.p[i].w2pc) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_pair2: the CTA-pair form needs the pair-layout weights");
   // expensive problems (large k) first: the last, partial wave of tiles is made of cheap ones
   std::stable_sort(L.p, L.p + L.nprob, [](const TcPairProb& a, const TcPairProb& b) { return a.k > b.k; });
   int most = 0;
@@ -464,11 +580,23 @@ int launch_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
       most = std::max(most, L.tiles_per_row[i] * L.B);
     }
   }
+  if (PAIR) most = (most + 1) / 2;       // a pair tile = two consecutive tiles of one problem
   const int total = most * L.nprob;      // round-robin index space (surplus indices of the problems with fewer tiles are skipped)
   L.ntiles = total;
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-  if (L.dbg) tc_pair2_kernel<N, true><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
-  else tc_pair2_kernel<N, false><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  if (PAIR) {
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    const int pairs = total < max_pairs ? total : max_pairs;
+    lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = Cfg::SMEM_BYTES; lc.stream = st; lc.attrs = la; lc.numAttrs = 1;
+    if (L.dbg) VTTS_CUDA(cudaLaunchKernelEx(&lc, tc_pair2_kernel<N, true, PAIR>, L));
+    else VTTS_CUDA(cudaLaunchKernelEx(&lc, tc_pair2_kernel<N, false, PAIR>, L));
+  } else {
+    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+    if (L.dbg) tc_pair2_kernel<N, true, PAIR><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+    else tc_pair2_kernel<N, false, PAIR><<<grid, NTHREADS, Cfg::SMEM_BYTES, st>>>(L);
+  }
   ctx->launches++;
   VTTS_CUDA(cudaGetLastError());
   return VTTS_OK;
@@ -476,7 +604,21 @@ int launch_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
 
 }  // namespace
 
-int vtts_launch_tc_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
+size_t vtts_tc_packed_pc_bytes(int k, int C) { return (size_t)k * C * C * 6; }   // 1.5 x the plain hi/lo packing
+
+int vtts_tc_pack_weights_pc(vtts_ctx* ctx, const float* w, void* dst, int k, int C) {
+  if (C % 16 != 0) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_pair2: C %d", C);
+  pack_w_pc_kernel<<<256, 256>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), k, C);
+  VTTS_CUDA(cudaGetLastError());
+  return VTTS_OK;
+}
+
+static int launch_pair2_any(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st, int pair);
+
+int vtts_launch_tc_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) { return launch_pair2_any(ctx, L, st, 0); }
+int vtts_launch_tc_pair2c(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) { return launch_pair2_any(ctx, L, st, 1); }
+
+static int launch_pair2_any(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st, int pair) {
   if (L.nprob < 1 || L.nprob > 3) return ctx->fail(VTTS_ERR_BAD_ARG, "tc_pair2: nprob %d", L.nprob);
   for (int i = 0; i < L.nprob; ++i) {
     const TcPairProb& p = L.p[i];
@@ -486,8 +628,8 @@ int vtts_launch_tc_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
   L.err = ctx->d_err;
   L.dbg = ctx->tc_dbg_on ? ctx->d_tc_dbg : nullptr;
   switch (L.N) {
-    case 64: return launch_pair2<64>(ctx, L, st);
-    case 32: return launch_pair2<32>(ctx, L, st);
+    case 64: return pair ? launch_pair2<64, 1>(ctx, L, st) : launch_pair2<64, 0>(ctx, L, st);
+    case 32: return pair ? launch_pair2<32, 1>(ctx, L, st) : launch_pair2<32, 0>(ctx, L, st);
     default: return ctx->fail(VTTS_ERR_BAD_ARG, "tc_pair2: N %d unsupported", L.N);
   }
 }

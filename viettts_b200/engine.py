@@ -108,11 +108,12 @@ class Engine:
                                           B, T, Cc, int(k), int(dil), float(slope), _ptr(out)))
         return out
 
-    PAIR_KERNELS = {"smem": 0, "tmem": 1, "smem2": 2}
+    PAIR_KERNELS = {"smem": 0, "tmem": 1, "smem2": 2, "smem2c": 3}
 
     def set_fused_pairs(self, on: bool, ts=None, kind: str | None = None):
         """Run the C <= 64 ResBlock pairs in a fused pair kernel (off: two tensor-core conv launches per pair).
-        kind: "smem2" tc_pair2.cu (two decoupled pipelines, A operand in shared memory; the default), "tmem"
+        kind: "smem2" tc_pair2.cu (two decoupled pipelines, A operand in shared memory; the default), "smem2c" the same kernel
+        in the CTA-pair form (cta_group::2 over clusters of two SMs, half of the weight operand per SM), "tmem"
         tc_pair_ts.cu (A operand in tensor memory), "smem" tc_pair.cu (first generation).  `ts` is the old spelling
         (True = "tmem", False = "smem")."""
         if kind is None:
