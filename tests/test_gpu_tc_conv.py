@@ -10,8 +10,13 @@ import torch
 from oracle import hifigan_oracle as ho
 from viettts_b200 import synthetic
 
+import os
+
 pytestmark = pytest.mark.gpu
 WAV_LINF, WAV_RMS = 1e-4, 1e-5
+# the optional CTA-pair form of the fused pair kernel ("smem2c", slower than the default) is exercised
+# only on request: VTTS_TEST_EXPERIMENTAL=1 (it passed every run of this suite while it was part of it)
+PAIR_KINDS = ["smem2", "tmem", "smem"] + (["smem2c"] if os.environ.get("VTTS_TEST_EXPERIMENTAL") == "1" else [])
 
 
 @pytest.fixture(scope="module")
@@ -95,7 +100,7 @@ def _ref_pair(x, w1, b1, w2, b2, k, dil, slope):
     return (y.transpose(1, 2) + xt).numpy()
 
 
-@pytest.mark.parametrize("ts", ["smem2", "smem2c", "tmem", "smem"])
+@pytest.mark.parametrize("ts", PAIR_KINDS)
 @pytest.mark.parametrize("C", [32, 64])
 @pytest.mark.parametrize("k,dil", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
 def test_fused_pair_vs_float64(eng, C, k, dil, ts):
@@ -120,7 +125,7 @@ def test_fused_pair_vs_float64(eng, C, k, dil, ts):
         assert err < 3e-4, (C, k, dil, bb, err)
 
 
-@pytest.mark.parametrize("ts", ["smem2", "smem2c", "tmem", "smem"])
+@pytest.mark.parametrize("ts", PAIR_KINDS)
 def test_fused_and_unfused_generator_agree(eng, hifigan_params, ts):
     mel = synthetic.mel_input(21, 2, 50)
     nf = np.array([50, 31], np.int32)
@@ -135,8 +140,10 @@ def test_fused_pair_long_rows_many_tiles(eng):
     """More tiles than SMs (the persistent loop wraps, every ring changes phase many times) and a length that ends
     inside a tile; C = 32 and 64 at the generator's own kernel sizes."""
     dev = torch.device("cuda", 0)
-    for kind, C, k, dil in (("smem2", 32, 7, 3), ("smem2", 64, 11, 5), ("smem2", 64, 3, 1), ("tmem", 32, 11, 5), ("tmem", 64, 7, 3),
-                            ("smem2c", 32, 7, 3), ("smem2c", 64, 11, 5), ("smem2c", 64, 3, 1), ("smem2c", 32, 3, 1)):
+    cases = [("smem2", 32, 7, 3), ("smem2", 64, 11, 5), ("smem2", 64, 3, 1), ("tmem", 32, 11, 5), ("tmem", 64, 7, 3)]
+    if "smem2c" in PAIR_KINDS:
+        cases += [("smem2c", 32, 7, 3), ("smem2c", 64, 11, 5), ("smem2c", 64, 3, 1), ("smem2c", 32, 3, 1)]
+    for kind, C, k, dil in cases:
         eng.set_fused_pairs(False, kind=kind)
         rng = np.random.default_rng(C + k)
         B, T = 4, 9000
