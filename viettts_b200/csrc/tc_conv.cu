@@ -517,8 +517,11 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
 template <int N, int EPI, int MT, int NPH, int STK = 0, int PAIR = 0>
 int launch_cfg(vtts_ctx* ctx, TcLaunch& L, cudaStream_t st) {
   using Cfg = TcCfg<N, MT, NPH, STK, PAIR>;
-  static bool attr_done = false;
-  static int max_pairs = 0;
+  // function attributes and cluster occupancy are per device (a process may hold contexts on several GPUs)
+  static bool attr_done_dev[64] = {};
+  static int max_pairs_dev[64] = {};
+  bool& attr_done = attr_done_dev[ctx->device & 63];
+  int& max_pairs = max_pairs_dev[ctx->device & 63];
   if (!attr_done) {
     VTTS_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N, EPI, MT, NPH, STK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (PAIR) {

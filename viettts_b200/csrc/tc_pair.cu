@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair_kernel(const __grid_const
 template <int N>
 int launch_pair(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
   using Cfg = PairCfg<N>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};   // function attributes are per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) {
     VTTS_CUDA(cudaFuncSetAttribute(tc_pair_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;

@@ -548,8 +548,11 @@ __global__ void pack_w_pc_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 template <int N, int PAIR = 0>
 int launch_pair2(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
   using Cfg = P2Cfg<N, PAIR>;
-  static bool attr_done = false;
-  static int max_pairs = 0;
+  // function attributes and cluster occupancy are per device (a process may hold contexts on several GPUs)
+  static bool attr_done_dev[64] = {};
+  static int max_pairs_dev[64] = {};
+  bool& attr_done = attr_done_dev[ctx->device & 63];
+  int& max_pairs = max_pairs_dev[ctx->device & 63];
   if (!attr_done) {
     VTTS_CUDA(cudaFuncSetAttribute(tc_pair2_kernel<N, false, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     VTTS_CUDA(cudaFuncSetAttribute(tc_pair2_kernel<N, true, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));

@@ -505,7 +505,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_pair_ts_kernel(const __grid_co
 template <int N>
 int launch_pair_ts(vtts_ctx* ctx, TcPairLaunch& L, cudaStream_t st) {
   using Cfg = TsCfg<N>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};   // function attributes are per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) {
     VTTS_CUDA(cudaFuncSetAttribute(tc_pair_ts_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     VTTS_CUDA(cudaFuncSetAttribute(tc_pair_ts_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
